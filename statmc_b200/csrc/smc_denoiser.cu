@@ -1,0 +1,398 @@
+// smc_denoiser.cu -- the denoise plan: validation, device descriptor tables, record storage, spatial table,
+// kernel selection and launch order.  Host-side replacement for cv::cuda::stat_denoiser::filter<T>
+// (stat_denoiser.cu:397-475) and for what Estimator::AllocateBuffers does with GpuMat pointer tables
+// (estimator.cpp:35-84, 271-288).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "smc_internal.h"
+
+struct smc_denoiser {
+    smc_context *ctx = nullptr;
+    int C = 3, ptr_count = 1, W = 0, H = 0, radius = 0, denoise_film = 0, mode = 0, n_gbufs = 0, NG = 0;
+    int row_begin = 0, row_end = 0;
+    int skip_top = 0, skip_bottom = 0;
+    int kernel_pref = 0;
+    float ds_factor = 0.f;
+    // device memory owned by the plan
+    SmcPtrStepSz *d_tables = nullptr;  // [n | mean | m2 | m3 | film_ptrs | mean_corr | disc | out | accepted][ptr_count] + gbufs
+    unsigned char *d_gch = nullptr;
+    float *d_gf = nullptr;
+    float *d_sw = nullptr;
+    int2 *d_rowrange = nullptr;
+    unsigned char *d_rec = nullptr;
+    bool tables_external = false;  // smc_filter_device_tables: tables live in caller memory
+    // resolved pointers
+    const SmcPtrStepSz *t_n = nullptr, *t_mean = nullptr, *t_m2 = nullptr, *t_m3 = nullptr, *t_film = nullptr,
+                       *t_gbufs = nullptr, *t_mc = nullptr, *t_disc = nullptr, *t_out = nullptr, *t_acc = nullptr;
+    SmcPtrStepSz film{}, film_filtered{};
+    int padX = 0, rec_pitch = 0, rec_rows = 0, sw_stride = 0;
+    size_t rec_image_stride = 0;
+    bool use_stream = false;
+    int py = 4;
+    char kernel_name[64] = "generic";
+};
+
+static int taps_in_window(int r) {
+    int c = 0;
+    for (int dy = -r; dy < r; dy++)
+        for (int dx = -r; dx < r; dx++)
+            if (dy * dy + dx * dx <= r * r) c++;
+    return c;
+}
+
+// Spatial table: sw[dy][dx] = dS2 * dSFactor * log2(e) for taps of the window [-r, r) x [-r, r) with
+// dS2 = dy^2 + dx^2 <= r^2 (SET_OUTER / SET_INNER, stat_denoiser.cu:24-37), -inf elsewhere (including the margins).
+static int build_spatial_table(smc_denoiser *d) {
+    const int r = d->radius, MY = SMC_SW_MARGIN_Y, MX = SMC_SW_MARGIN_X;
+    const int rows = 2 * r + 2 * MY;
+    d->sw_stride = 2 * r + 2 * MX;
+    std::vector<float> sw((size_t)rows * d->sw_stride, -INFINITY);
+    std::vector<int2> rr(rows);
+    for (int tr = 0; tr < rows; tr++) {
+        const int dy = tr - r - MY;
+        rr[tr] = make_int2(1 << 20, -(1 << 20));
+        if (dy < -r || dy > r - 1) continue;
+        int lo = 1 << 20, hi = -(1 << 20);
+        for (int dx = -r; dx <= r - 1; dx++) {
+            const int dS2 = dy * dy + dx * dx;
+            if (dS2 > r * r) continue;
+            // float(dS2) * dSFactor as the reference forms it, then the change of base in double, rounded once
+            sw[(size_t)tr * d->sw_stride + (dx + r + MX)] = (float)((double)dS2 * (double)d->ds_factor * 1.4426950408889634);
+            lo = std::min(lo, dx);
+            hi = std::max(hi, dx);
+        }
+        if (lo <= hi) rr[tr] = make_int2(lo, hi + 1);  // +1: the thread's second column sees dx = j - 1
+    }
+    SMC_CUDA(cudaMalloc(&d->d_sw, sw.size() * sizeof(float)));
+    SMC_CUDA(cudaMalloc(&d->d_rowrange, rr.size() * sizeof(int2)));
+    SMC_CUDA(cudaMemcpyAsync(d->d_sw, sw.data(), sw.size() * sizeof(float), cudaMemcpyHostToDevice, d->ctx->stream));
+    SMC_CUDA(cudaMemcpyAsync(d->d_rowrange, rr.data(), rr.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                             d->ctx->stream));
+    SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));  // sources are stack/pageable
+    return SMC_OK;
+}
+
+static int alloc_records(smc_denoiser *d) {
+    const int r = d->radius;
+    d->padX = ((r + 15) / 16) * 16;
+    if (d->padX == 0) d->padX = 16;
+    d->rec_pitch = ((d->W + 2 * d->padX + 15) / 16) * 16;
+    d->rec_rows = d->H + 2 * r + 4;  // +4: rows only ever paired with out-of-range centre rows of the last tile
+    d->rec_image_stride = (size_t)d->rec_rows * smc_rec_row_bytes(d->rec_pitch);
+    const size_t bytes = d->rec_image_stride * d->ptr_count;
+    cudaError_t e = cudaMalloc(&d->d_rec, bytes);
+    if (e != cudaSuccess)
+        SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu bytes of records) failed: %s", bytes, cudaGetErrorString(e));
+    SMC_CUDA(cudaMemsetAsync(d->d_rec, 0, bytes, d->ctx->stream));
+    return SMC_OK;
+}
+
+static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p) {
+    p.W = d->W; p.H = d->H; p.C = d->C; p.NG = d->NG; p.radius = d->radius; p.mode = d->mode;
+    p.ptr_count = d->ptr_count; p.denoise_film = d->denoise_film;
+    p.row_begin = d->row_begin; p.row_end = d->row_end;
+    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec;
+    p.sw = d->d_sw; p.sw_stride = d->sw_stride; p.sw_margin_y = SMC_SW_MARGIN_Y; p.sw_margin_x = SMC_SW_MARGIN_X;
+    p.out_ptrs = d->t_out; p.film_filtered = d->film_filtered; p.accepted = d->t_acc;
+}
+
+static int select_kernel(smc_denoiser *d) {
+    SmcFilterParams p;
+    fill_filter_params(d, p);
+    const char *nm = nullptr;
+    const bool ok = smc_filter_stream_supported(p, d->ctx->sm_count, &nm);
+    if (d->kernel_pref == 2 && !ok)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming kernel requested but not available for C=%d NG=%d r=%d", d->C, d->NG,
+                 d->radius);
+    d->use_stream = ok && d->kernel_pref != 1;
+    d->py = 4;
+    if (const char *e = getenv("SMC_STREAM_PY")) d->py = atoi(e) == 2 ? 2 : 4;
+    snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", d->use_stream ? "stream" : "generic");
+    return SMC_OK;
+}
+
+static int validate_common(int channels, int ptr_count, int width, int height, int radius, int n_gbufs) {
+    if (channels != 1 && channels != 3) SMC_FAIL(SMC_ERR_INVALID, "channels must be 1 or 3, got %d", channels);
+    if (ptr_count < 1 || ptr_count > SMC_MAX_DIM) SMC_FAIL(SMC_ERR_INVALID, "ptr_count %d out of range", ptr_count);
+    if (width < 1 || height < 1 || width > SMC_MAX_DIM || height > SMC_MAX_DIM)
+        SMC_FAIL(SMC_ERR_INVALID, "size %d x %d out of range (reference: unsigned short)", width, height);
+    if (radius < 0 || radius > SMC_MAX_RADIUS)
+        SMC_FAIL(SMC_ERR_INVALID, "radius %d out of range (reference: unsigned char)", radius);
+    if (n_gbufs < 0 || n_gbufs > 255) SMC_FAIL(SMC_ERR_INVALID, "n_gbufs %d out of range", n_gbufs);
+    return SMC_OK;
+}
+
+static bool plane_ok(const smc_plane *arr, int count) {
+    if (!arr) return false;
+    for (int i = 0; i < count; i++)
+        if (!arr[i].dev) return false;
+    return true;
+}
+
+extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc, smc_denoiser **out) {
+    if (!ctx || !desc || !out) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = validate_common(desc->channels, desc->ptr_count, desc->width, desc->height, desc->radius, desc->n_gbufs);
+    if (rc) return rc;
+    if (desc->membership != SMC_MEMBER_WELCH && desc->membership != SMC_MEMBER_MOON)
+        SMC_FAIL(SMC_ERR_INVALID, "bad membership %d", desc->membership);
+    const int pc = desc->ptr_count;
+    if (!plane_ok(desc->n, pc) || !plane_ok(desc->mean, pc) || !plane_ok(desc->m2, pc))
+        SMC_FAIL(SMC_ERR_INVALID, "n/mean/m2 planes are required for every image");
+    if (desc->membership == SMC_MEMBER_WELCH && !plane_ok(desc->m3, pc))
+        SMC_FAIL(SMC_ERR_INVALID, "m3 planes are required for the Welch membership");
+    if (!plane_ok(desc->film_ptrs, pc) && !(desc->channels == 3 && desc->denoise_film && pc == 1))
+        SMC_FAIL(SMC_ERR_INVALID, "film_ptrs planes are required");
+    if (!plane_ok(desc->film_filtered_ptrs, pc) && !(desc->channels == 3 && desc->denoise_film && pc == 1))
+        SMC_FAIL(SMC_ERR_INVALID, "film_filtered_ptrs planes are required");
+    if (desc->denoise_film && (!desc->film.dev || !desc->film_filtered.dev))
+        SMC_FAIL(SMC_ERR_INVALID, "denoise_film needs film and film_filtered");
+    int ng = 0;
+    for (int g = 0; g < desc->n_gbufs; g++) {
+        if (!desc->gbufs || !desc->gbufs[g].dev || !desc->gbuf_channels || !desc->gbuf_dr_factors)
+            SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d incomplete", g);
+        // the reference silently ignores channel counts other than 1 and 3 (stat_denoiser.cu:103-110); we reject them
+        if (desc->gbuf_channels[g] != 1 && desc->gbuf_channels[g] != 3)
+            SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d has %d channels (1 or 3 supported)", g, desc->gbuf_channels[g]);
+        if (!(desc->gbuf_dr_factors[g] <= 0.f))
+            SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d: drFactor %g must be <= 0 (-0.5/sd^2)", g, desc->gbuf_dr_factors[g]);
+        ng += desc->gbuf_channels[g];
+    }
+    if (ng > SMC_MAX_GBUF_CHANNELS)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "%d flattened G-buffer channels; this build handles %d", ng, SMC_MAX_GBUF_CHANNELS);
+    int rb = desc->row_begin, re = desc->row_end;
+    if (rb == 0 && re == 0) re = desc->height;
+    if (rb < 0 || re > desc->height || rb > re) SMC_FAIL(SMC_ERR_INVALID, "bad row range [%d, %d)", rb, re);
+
+    SMC_CUDA(cudaSetDevice(ctx->device));
+    smc_denoiser *d = new (std::nothrow) smc_denoiser;
+    if (!d) SMC_FAIL(SMC_ERR_NOMEM, "out of host memory");
+    d->ctx = ctx; d->C = desc->channels; d->ptr_count = pc; d->W = desc->width; d->H = desc->height;
+    d->radius = desc->radius; d->denoise_film = desc->denoise_film ? 1 : 0; d->mode = desc->membership;
+    d->n_gbufs = desc->n_gbufs; d->NG = ng; d->row_begin = rb; d->row_end = re; d->ds_factor = desc->ds_factor;
+    d->skip_top = desc->halo_top_external ? 1 : 0; d->skip_bottom = desc->halo_bottom_external ? 1 : 0;
+    d->kernel_pref = desc->kernel;
+
+    // descriptor tables: 9 per-image families + G-buffers, one allocation
+    const int fam = 9;
+    std::vector<SmcPtrStepSz> h((size_t)fam * pc + std::max(desc->n_gbufs, 1));
+    const smc_plane *src[fam] = {desc->n, desc->mean, desc->m2, desc->m3, desc->film_ptrs, desc->mean_corr,
+                                 desc->disc, desc->film_filtered_ptrs, desc->accepted};
+    for (int f = 0; f < fam; f++)
+        for (int i = 0; i < pc; i++) {
+            SmcPtrStepSz &e = h[(size_t)f * pc + i];
+            e.data = src[f] ? (unsigned char *)src[f][i].dev : nullptr;
+            e.step = src[f] ? src[f][i].step : 0;
+            e.cols = d->W;
+            e.rows = d->H;
+        }
+    for (int g = 0; g < desc->n_gbufs; g++) {
+        SmcPtrStepSz &e = h[(size_t)fam * pc + g];
+        e.data = (unsigned char *)desc->gbufs[g].dev;
+        e.step = desc->gbufs[g].step;
+        e.cols = d->W;
+        e.rows = d->H;
+    }
+    auto fail = [&](int code) {
+        smc_denoiser_destroy(d);
+        return code;
+    };
+    if (cudaMalloc(&d->d_tables, h.size() * sizeof(SmcPtrStepSz)) != cudaSuccess ||
+        cudaMalloc(&d->d_gch, std::max(desc->n_gbufs, 1)) != cudaSuccess ||
+        cudaMalloc(&d->d_gf, sizeof(float) * std::max(desc->n_gbufs, 1)) != cudaSuccess) {
+        smc_set_error("cudaMalloc(descriptor tables) failed");
+        return fail(SMC_ERR_NOMEM);
+    }
+    cudaMemcpyAsync(d->d_tables, h.data(), h.size() * sizeof(SmcPtrStepSz), cudaMemcpyHostToDevice, ctx->stream);
+    if (desc->n_gbufs > 0) {
+        cudaMemcpyAsync(d->d_gch, desc->gbuf_channels, desc->n_gbufs, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d->d_gf, desc->gbuf_dr_factors, sizeof(float) * desc->n_gbufs, cudaMemcpyHostToDevice,
+                        ctx->stream);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        smc_set_error("uploading descriptor tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(SMC_ERR_CUDA);
+    }
+    d->t_n = d->d_tables + 0 * pc; d->t_mean = d->d_tables + 1 * pc; d->t_m2 = d->d_tables + 2 * pc;
+    d->t_m3 = d->d_tables + 3 * pc; d->t_film = d->d_tables + 4 * pc;
+    d->t_mc = desc->mean_corr ? d->d_tables + 5 * pc : nullptr;
+    d->t_disc = desc->disc ? d->d_tables + 6 * pc : nullptr;
+    d->t_out = d->d_tables + 7 * pc;
+    d->t_acc = desc->accepted ? d->d_tables + 8 * pc : nullptr;
+    d->t_gbufs = d->d_tables + (size_t)fam * pc;
+    d->film = SmcPtrStepSz{(unsigned char *)desc->film.dev, desc->film.step, d->W, d->H};
+    d->film_filtered = SmcPtrStepSz{(unsigned char *)desc->film_filtered.dev, desc->film_filtered.step, d->W, d->H};
+
+    if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = select_kernel(d))) return fail(rc);
+    *out = d;
+    return SMC_OK;
+}
+
+extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (!d->tables_external) cudaFree(d->d_tables);
+    cudaFree(d->d_gch);
+    cudaFree(d->d_gf);
+    cudaFree(d->d_sw);
+    cudaFree(d->d_rowrange);
+    cudaFree(d->d_rec);
+    delete d;
+}
+
+extern "C" int smc_denoiser_prepass(smc_denoiser *d) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    SMC_CUDA(cudaSetDevice(d->ctx->device));
+    SmcPrepassParams p;
+    p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->ptr_count; p.radius = d->radius; p.mode = d->mode;
+    p.denoise_film = d->denoise_film; p.padX = d->padX; p.rec_pitch = d->rec_pitch;
+    p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec; p.skip_top = d->skip_top; p.skip_bottom = d->skip_bottom;
+    p.n = d->t_n; p.mean = d->t_mean; p.m2 = d->t_m2; p.m3 = d->t_m3; p.film_ptrs = d->t_film; p.film = d->film;
+    p.n_gbufs = d->n_gbufs; p.gbufs = d->t_gbufs; p.gbuf_channels = d->d_gch; p.gbuf_dr_factors = d->d_gf;
+    p.mean_corr = d->t_mc; p.disc = d->t_disc; p.lut = d->ctx->d_lut;
+    return smc_launch_prepass(d->ctx, p);
+}
+
+extern "C" int smc_denoiser_filter(smc_denoiser *d) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    SMC_CUDA(cudaSetDevice(d->ctx->device));
+    SmcFilterParams p;
+    fill_filter_params(d, p);
+    if (d->use_stream) {
+        const char *nm = nullptr;
+        const int rc = smc_launch_filter_stream(d->ctx, p, d->d_rowrange, d->py, &nm);
+        if (nm) snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", nm);
+        return rc;
+    }
+    snprintf(d->kernel_name, sizeof(d->kernel_name), "generic<C=%d,NG=%d,%s>", d->C, d->NG, d->mode ? "moon" : "welch");
+    return smc_launch_filter_generic(d->ctx, p);
+}
+
+extern "C" int smc_denoiser_run(smc_denoiser *d) {
+    int rc = smc_denoiser_prepass(d);
+    if (rc) return rc;
+    return smc_denoiser_filter(d);
+}
+
+extern "C" int smc_denoiser_halo(smc_denoiser *d, int z, int which, void **dev, size_t *bytes) {
+    if (!d || !dev || !bytes) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    if (z < 0 || z >= d->ptr_count) SMC_FAIL(SMC_ERR_INVALID, "image %d out of range", z);
+    const int r = d->radius;
+    if (r > d->H) SMC_FAIL(SMC_ERR_UNSUPPORTED, "band of %d rows is shorter than the radius %d", d->H, r);
+    const size_t row_bytes = smc_rec_row_bytes(d->rec_pitch);
+    unsigned char *img = d->d_rec + (size_t)z * d->rec_image_stride;
+    int first;  // record row (record row k holds y = k - r)
+    switch (which) {
+        case 0: first = r; break;                 // own rows 0 .. r-1
+        case 1: first = d->H; break;              // own rows H-r .. H-1  -> record rows H .. H+r-1
+        case 2: first = 0; break;                 // halo above: y = -r .. -1
+        case 3: first = d->H + r; break;          // halo below: y = H .. H+r-1
+        default: SMC_FAIL(SMC_ERR_INVALID, "which must be 0..3");
+    }
+    *dev = img + (size_t)first * row_bytes;
+    *bytes = (size_t)r * row_bytes;
+    return SMC_OK;
+}
+
+extern "C" uint64_t smc_denoiser_pairs(const smc_denoiser *d) {
+    if (!d) return 0;
+    return (uint64_t)(d->row_end - d->row_begin) * (uint64_t)d->W * (uint64_t)taps_in_window(d->radius) *
+           (uint64_t)d->ptr_count;
+}
+
+extern "C" size_t smc_denoiser_record_bytes(const smc_denoiser *d) { return d ? d->rec_image_stride * d->ptr_count : 0; }
+extern "C" const char *smc_denoiser_kernel_name(const smc_denoiser *d) { return d ? d->kernel_name : ""; }
+
+// ---------------------------------------------------------------------------------------------------------
+// One-shot entry point with the reference's device-resident descriptor tables (cudaimgproc.hpp:756-777).
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_count, int width, int height,
+                                        float ds_factor, int radius, int denoise_film, const void *n_ptrs,
+                                        const void *mean_ptrs, const void *m2_ptrs, const void *m3_ptrs,
+                                        const void *film_ptrs, const void *film_data, size_t film_step,
+                                        const void *gbuf_ptrs, const void *gbuf_channel_counts,
+                                        const void *gbuf_dr_factors, int n_gbufs, void *mean_corr_ptrs,
+                                        void *disc_ptrs, void *film_filtered_ptrs, void *film_filtered_data,
+                                        size_t film_filtered_step, void *stream) {
+    if (!ctx) SMC_FAIL(SMC_ERR_INVALID, "ctx == NULL");
+    int rc = validate_common(channels, ptr_count, width, height, radius, n_gbufs);
+    if (rc) return rc;
+    if (!n_ptrs || !mean_ptrs || !m2_ptrs || !m3_ptrs || !film_ptrs || !film_filtered_ptrs)
+        SMC_FAIL(SMC_ERR_INVALID, "NULL descriptor table");
+    if (denoise_film && (!film_data || !film_filtered_data)) SMC_FAIL(SMC_ERR_INVALID, "denoiseFilm needs film buffers");
+    if (n_gbufs > 0 && (!gbuf_ptrs || !gbuf_channel_counts || !gbuf_dr_factors))
+        SMC_FAIL(SMC_ERR_INVALID, "NULL G-buffer table");
+    SMC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+
+    // The kernel variant depends on the G-buffer channel counts, which live on the device: read them back once per
+    // distinct (pointer, count, shape) and cache the plan on the context (Estimator never changes them after
+    // AllocateBuffers, estimator.cpp:271-288).
+    std::vector<unsigned char> key(sizeof(void *) * 2 + sizeof(int) * 8 + sizeof(float));
+    {
+        unsigned char *k = key.data();
+        std::memcpy(k, &gbuf_channel_counts, sizeof(void *)); k += sizeof(void *);
+        std::memcpy(k, &gbuf_dr_factors, sizeof(void *)); k += sizeof(void *);
+        const int ints[8] = {channels, ptr_count, width, height, radius, denoise_film, n_gbufs, 0};
+        std::memcpy(k, ints, sizeof(ints)); k += sizeof(ints);
+        std::memcpy(k, &ds_factor, sizeof(float));
+    }
+    smc_denoiser *d = ctx->cached;
+    if (!d || key != ctx->cached_key) {
+        if (d) smc_denoiser_destroy(d);
+        ctx->cached = nullptr;
+        std::vector<unsigned char> gch(std::max(n_gbufs, 1));
+        std::vector<float> gf(std::max(n_gbufs, 1));
+        if (n_gbufs > 0) {
+            SMC_CUDA(cudaMemcpyAsync(gch.data(), gbuf_channel_counts, n_gbufs, cudaMemcpyDeviceToHost, s));
+            SMC_CUDA(cudaMemcpyAsync(gf.data(), gbuf_dr_factors, sizeof(float) * n_gbufs, cudaMemcpyDeviceToHost, s));
+            SMC_CUDA(cudaStreamSynchronize(s));
+        }
+        int ng = 0;
+        for (int g = 0; g < n_gbufs; g++) {
+            if (gch[g] != 1 && gch[g] != 3) SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d has %d channels", g, gch[g]);
+            if (!(gf[g] <= 0.f)) SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d: drFactor %g must be <= 0", g, gf[g]);
+            ng += gch[g];
+        }
+        if (ng > SMC_MAX_GBUF_CHANNELS) SMC_FAIL(SMC_ERR_UNSUPPORTED, "%d flattened G-buffer channels", ng);
+        d = new (std::nothrow) smc_denoiser;
+        if (!d) SMC_FAIL(SMC_ERR_NOMEM, "out of host memory");
+        d->ctx = ctx; d->C = channels; d->ptr_count = ptr_count; d->W = width; d->H = height; d->radius = radius;
+        d->denoise_film = denoise_film ? 1 : 0; d->mode = SMC_MEMBER_WELCH; d->n_gbufs = n_gbufs; d->NG = ng;
+        d->row_begin = 0; d->row_end = height; d->ds_factor = ds_factor; d->tables_external = true;
+        if (cudaMalloc(&d->d_gch, std::max(n_gbufs, 1)) != cudaSuccess ||
+            cudaMalloc(&d->d_gf, sizeof(float) * std::max(n_gbufs, 1)) != cudaSuccess) {
+            smc_denoiser_destroy(d);
+            SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc failed");
+        }
+        if (n_gbufs > 0) {
+            cudaMemcpy(d->d_gch, gch.data(), n_gbufs, cudaMemcpyHostToDevice);
+            cudaMemcpy(d->d_gf, gf.data(), sizeof(float) * n_gbufs, cudaMemcpyHostToDevice);
+        }
+        if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = select_kernel(d))) {
+            smc_denoiser_destroy(d);
+            return rc;
+        }
+        SMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->cached = d;
+        ctx->cached_key = key;
+    }
+    d->t_n = (const SmcPtrStepSz *)n_ptrs; d->t_mean = (const SmcPtrStepSz *)mean_ptrs;
+    d->t_m2 = (const SmcPtrStepSz *)m2_ptrs; d->t_m3 = (const SmcPtrStepSz *)m3_ptrs;
+    d->t_film = (const SmcPtrStepSz *)film_ptrs; d->t_gbufs = (const SmcPtrStepSz *)gbuf_ptrs;
+    d->t_mc = (const SmcPtrStepSz *)mean_corr_ptrs; d->t_disc = (const SmcPtrStepSz *)disc_ptrs;
+    d->t_out = (const SmcPtrStepSz *)film_filtered_ptrs; d->t_acc = nullptr;
+    d->film = SmcPtrStepSz{(unsigned char *)film_data, film_step, width, height};
+    d->film_filtered = SmcPtrStepSz{(unsigned char *)film_filtered_data, film_filtered_step, width, height};
+    // run on the caller's stream
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = s;
+    rc = smc_denoiser_run(d);
+    ctx->stream = saved;
+    return rc;
+}

@@ -1,0 +1,385 @@
+// smc_filter_stream.cu -- the B200 filter kernel: membership-gated cross-bilateral filtering of RGB statistics
+// (filter_kernel<float3>, stat_denoiser.cu:276-345) restructured around the SM's FP32 pipes instead of its LSUs.
+//
+// The reference runs one thread per pixel and re-reads ~15 floats per tap from global/L1 (2r x 2r taps).  Here:
+//   * a persistent CTA (4 warps) owns a tile of 256 x PY output pixels; each thread owns 2 x PY of them and keeps
+//     their centre statistics and accumulators in registers;
+//   * the record rows the tile needs (y0-r .. y0+PY-1+r-1, 256+2r records wide) stream through a ring of shared
+//     memory slots filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP) issued by one
+//     elected thread, D-1 rows ahead of the consumers; the record array is already border-replicated and
+//     line-padded by the prepass, so a slot is a verbatim copy, every LDS.128 is bank-conflict-free and its address
+//     is `register + immediate`;
+//   * every record a thread loads (4 x LDS.128) is used for its 2 x PY centre pixels, i.e. 0.5 (PY=4) LDS.128 per
+//     pair evaluation; per pair the math is ~21 issue slots / ~24 FP32 lane-cycles using packed FADD2/FMUL2/FFMA2.
+// Work is compute-bound (1255 pair evaluations per pixel at r = 20 against 64 B of record traffic), so the roofline
+// is the FP32 pipe: see DESIGN.md.
+#include <algorithm>
+#include <cmath>
+
+#include "smc_filter_math.cuh"
+#include "smc_internal.h"
+
+namespace {
+
+constexpr int kTileW = 256;
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+
+struct StreamGeom {
+    int tiles_x, tiles_y;
+    int total_tiles;
+    int nr;              // record rows per tile = 2r + PY - 1
+    int depth;           // ring slots
+    int slot_bytes;      // bytes per ring slot (multiple of 128)
+    int seg_max_rec;     // records per full segment (even)
+    int sw_rows;         // rows of the spatial table
+    const int2 *rowrange;  // per table row: {jlo, jhi} (device)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ SmcRec lds_rec(const unsigned char *p) {
+    SmcRec r;
+    r.c0 = *(const float4 *)(p);
+    r.c1 = *(const float4 *)(p + 16);
+    r.c2 = *(const float4 *)(p + 32);
+    r.c3 = *(const float4 *)(p + 48);
+    return r;
+}
+__device__ __forceinline__ SmcRec ldg_rec(const unsigned char *row, int pcol) {
+    const unsigned char *p = row + smc_rec_offset(pcol);
+    SmcRec r;
+    r.c0 = __ldg((const float4 *)(p));
+    r.c1 = __ldg((const float4 *)(p + 16));
+    r.c2 = __ldg((const float4 *)(p + 32));
+    r.c3 = __ldg((const float4 *)(p + 48));
+    return r;
+}
+
+struct Acc {
+    float n0, n1, n2, den;
+    int cnt;
+};
+
+template <int NG, int MODE, bool COUNT>
+__device__ __forceinline__ void pair_eval(const SmcCentre<3, NG> &c, const SmcRec &r, float sw, Acc &a) {
+    const bool ok = smc_member<3, NG, MODE>(c, r);
+    const float w = smc_weight<3, NG>(c, r, sw);
+    if (ok) {
+        a.n0 = __fmaf_rn(w, r.c2.x, a.n0);
+        a.n1 = __fmaf_rn(w, r.c2.y, a.n1);
+        a.n2 = __fmaf_rn(w, r.c1.z, a.n2);
+        a.den = __fadd_rn(a.den, w);
+        // a tap outside the window has sw = -inf -> w = 0: it adds nothing, but must not be counted
+        if (COUNT) a.cnt += (sw != -INFINITY) ? 1 : 0;
+    }
+}
+
+struct TileCoord {
+    int z, x0, y0;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int t, const StreamGeom &g, int row_begin, int PY) {
+    TileCoord c;
+    const int per_img = g.tiles_x * g.tiles_y;
+    c.z = t / per_img;
+    const int rem = t - c.z * per_img;
+    const int ty = rem / g.tiles_x;
+    c.x0 = (rem - ty * g.tiles_x) * kTileW;
+    c.y0 = row_begin + ty * PY;
+    return c;
+}
+
+// first record (even) of the row segment a tile stages
+__device__ __forceinline__ int seg_start_of(const SmcFilterParams &p, int x0) { return (x0 + p.padX - p.radius) & ~1; }
+
+// source address / size of record row `i` (0..nr-1) of a tile; record row k of the array holds y = k - r
+__device__ __forceinline__ void seg_of(const SmcFilterParams &p, const TileCoord &tc, int i, const unsigned char *&src,
+                                       uint32_t &bytes, int seg_max_rec) {
+    const int seg_start = seg_start_of(p, tc.x0);
+    const int nrec = min(seg_max_rec, p.rec_pitch - seg_start);  // even
+    src = p.rec + (size_t)tc.z * p.rec_image_stride + (size_t)(tc.y0 + i) * smc_rec_row_bytes(p.rec_pitch) +
+          smc_rec_offset(seg_start);
+    bytes = (uint32_t)(nrec / 2) * SMC_LINE_BYTES;
+}
+
+template <int NG, int PY, int MODE, bool COUNT>
+__global__ void __launch_bounds__(kThreads, 2) filter_stream_kernel(const SmcFilterParams p, const StreamGeom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [ring: depth * slot_bytes][sw table: sw_rows * sw_stride floats][rowrange: sw_rows int2][barriers]
+    unsigned char *ring = smem;
+    float *sw = (float *)(ring + (size_t)g.depth * g.slot_bytes);
+    int2 *rowrange = (int2 *)(sw + g.sw_rows * p.sw_stride);
+    uint64_t *full = (uint64_t *)(rowrange + g.sw_rows);
+    uint64_t *empty = full + g.depth;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = p.radius;
+    const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
+
+    for (int i = threadIdx.x; i < g.sw_rows * p.sw_stride; i += kThreads) sw[i] = p.sw[i];
+    for (int i = threadIdx.x; i < g.sw_rows; i += kThreads) rowrange[i] = g.rowrange[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.depth; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_tiles = (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (my_tiles <= 0) return;
+    const long long total_pos = (long long)my_tiles * g.nr;  // positions of this CTA's row stream
+    const bool producer = (threadIdx.x == 0);
+
+    // issue the copy for stream position `q`
+    auto issue = [&](long long q) {
+        const int tl = (int)(q / g.nr), i = (int)(q - (long long)tl * g.nr);
+        const TileCoord tc = tile_coord((int)blockIdx.x + tl * (int)gridDim.x, g, p.row_begin, PY);
+        const unsigned char *src;
+        uint32_t bytes;
+        seg_of(p, tc, i, src, bytes, g.seg_max_rec);
+        const int s = (int)(q % g.depth);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(ring + (size_t)s * g.slot_bytes, src, bytes, &full[s]);
+    };
+    if (producer)
+        for (long long q = 0; q < min((long long)g.depth, total_pos); q++) issue(q);
+
+    long long pos = 0;
+    for (int tl = 0; tl < my_tiles; tl++) {
+        const TileCoord tc = tile_coord((int)blockIdx.x + tl * (int)gridDim.x, g, p.row_begin, PY);
+        const unsigned char *img = p.rec + (size_t)tc.z * p.rec_image_stride;
+        const int xf = tc.x0 + warp * 64 + 2 * lane;  // first of this thread's two columns
+        const bool warp_active = tc.x0 + warp * 64 < p.W;
+        const int base_idx = xf + p.padX - seg_start_of(p, tc.x0);  // slot index of the record at dx = 0, column kx = 0
+
+        SmcCentre<3, NG> cen[PY][2];
+        Acc acc[PY][2];
+#pragma unroll
+        for (int ky = 0; ky < PY; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+                const int yc = min(tc.y0 + ky, p.H - 1), xc = min(xf + kx, p.W - 1);
+                const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, xc + p.padX);
+                smc_make_centre<3, NG, MODE>(rc, cen[ky][kx]);
+                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = 0.f;
+                acc[ky][kx].cnt = 0;
+            }
+
+        for (int i = 0; i < g.nr; i++, pos++) {
+            const int s = (int)(pos % g.depth);
+            const uint32_t parity = (uint32_t)((pos / g.depth) & 1);
+            mbar_wait(&full[s], parity);
+            if (warp_active) {
+                // table row of centre row ky: dy = i - r - ky  ->  row index dy + r + margin_y = i - ky + margin_y
+                int lo = 1 << 20, hi = -(1 << 20);
+#pragma unroll
+                for (int ky = 0; ky < PY; ky++) {
+                    const int2 rr = rowrange[i - ky + p.sw_margin_y];
+                    lo = min(lo, rr.x);
+                    hi = max(hi, rr.y);
+                }
+                if (lo <= hi) {
+                    // pointer to sw[row of ky = 0][dx = lo]; the rows of ky = 1.. are sw_stride floats lower each
+                    const float *swp = sw + (i + p.sw_margin_y) * p.sw_stride + (r + p.sw_margin_x) + lo;
+                    const int sws = p.sw_stride;
+                    float sw_prev[PY];
+#pragma unroll
+                    for (int ky = 0; ky < PY; ky++) sw_prev[ky] = swp[-ky * sws - 1];
+                    // records base_idx+lo, +1, ...: byte offsets alternate +64 / +80 (two records + pad per 144-B line)
+                    const int first = base_idx + lo;
+                    const unsigned char *rp = ring + (size_t)s * g.slot_bytes + smc_rec_offset(first);
+                    const int d0 = (first & 1) ? SMC_LINE_BYTES - SMC_REC_BYTES : SMC_REC_BYTES;
+                    const int d1 = SMC_LINE_BYTES - d0;
+                    SmcRec cur = lds_rec(rp);
+                    int j = lo;
+                    for (; j + 1 <= hi; j += 2) {
+                        const SmcRec nxt = lds_rec(rp + d0);
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);       // dx = j
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);  // dx = j - 1
+                            sw_prev[ky] = sw_cur;
+                        }
+                        rp += SMC_LINE_BYTES;
+                        cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws + 1];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], nxt, sw_cur, acc[ky][0]);       // dx = j + 1
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], nxt, sw_prev[ky], acc[ky][1]);  // dx = j
+                            sw_prev[ky] = sw_cur;
+                        }
+                        swp += 2;
+                    }
+                    if (j <= hi) {
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);
+                        }
+                    }
+                    (void)d1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            // refill with a lag of one row: the slot of position pos-1 is free once every warp has left it
+            if (producer && pos >= 1 && pos - 1 + g.depth < total_pos) {
+                const long long q = pos - 1;
+                mbar_wait(&empty[(int)(q % g.depth)], (uint32_t)((q / g.depth) & 1));
+                issue(q + g.depth);
+            }
+        }
+
+        // write the tile (stat_denoiser.cu:341-344); centre fix-up: the reference gives the centre tap weight 1
+        // unconditionally (:318-323), the loop above only if the centre passes its own test (it does unless NaN).
+        const SmcPtrStepSz o = (p.denoise_film && tc.z == 0) ? p.film_filtered : p.out_ptrs[tc.z];
+#pragma unroll
+        for (int ky = 0; ky < PY; ky++) {
+            const int y = tc.y0 + ky;
+            if (y >= p.row_end) continue;
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+                const int x = xf + kx;
+                if (x >= p.W) continue;
+                Acc a = acc[ky][kx];
+                const SmcRec rc = ldg_rec(img + (size_t)(y + r) * row_bytes, x + p.padX);
+                if (!smc_member<3, NG, MODE>(cen[ky][kx], rc)) {
+                    a.n0 = __fadd_rn(a.n0, rc.c2.x);
+                    a.n1 = __fadd_rn(a.n1, rc.c2.y);
+                    a.n2 = __fadd_rn(a.n2, rc.c1.z);
+                    a.den = __fadd_rn(a.den, 1.f);
+                    a.cnt += 1;
+                }
+                float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
+                op[0] = __fdiv_rn(a.n0, a.den);
+                op[1] = __fdiv_rn(a.n1, a.den);
+                op[2] = __fdiv_rn(a.n2, a.den);
+                if (COUNT && p.accepted && p.accepted[tc.z].data)
+                    ((int *)(p.accepted[tc.z].data + (size_t)y * p.accepted[tc.z].step))[x] = a.cnt;
+            }
+        }
+    }
+}
+
+template <int NG, int PY, int MODE>
+int launch(smc_context *ctx, const SmcFilterParams &p, const StreamGeom &g, int grid, size_t smem) {
+    const bool count = p.accepted != nullptr;
+    if (count) {
+        auto k = filter_stream_kernel<NG, PY, MODE, true>;
+        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
+    } else {
+        auto k = filter_stream_kernel<NG, PY, MODE, false>;
+        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
+    }
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
+}
+
+}  // namespace
+
+// geometry shared by the support check and the launcher
+static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, size_t &smem) {
+    const int rows = p.row_end - p.row_begin;
+    g.tiles_x = (p.W + kTileW - 1) / kTileW;
+    g.tiles_y = (rows + PY - 1) / PY;
+    const long long total = (long long)g.tiles_x * g.tiles_y * p.ptr_count;
+    if (total <= 0 || total > 0x7fffffffLL) return false;
+    g.total_tiles = (int)total;
+    g.nr = 2 * p.radius + PY - 1;
+    // widest reach: first record x0 - r (rounded down to even), last x0 + 255 + r, plus one prefetched past the end
+    g.seg_max_rec = kTileW + 2 * p.radius + 4;
+    g.slot_bytes = (((g.seg_max_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
+    g.sw_rows = 2 * p.radius + 2 * p.sw_margin_y;
+    const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 2 * 8 * 8 + 64;
+    // prefer 2 CTAs per SM (2 x (smem + 1 KB reserved) <= 227 KB), ring depth 4 then 3
+    smem = 0;
+    for (int depth = 4; depth >= 3; depth--) {
+        const size_t s = (size_t)depth * g.slot_bytes + fixed;
+        if (2 * (s + 1024) <= 227 * 1024 || depth == 3) {
+            g.depth = depth;
+            smem = s;
+            break;
+        }
+    }
+    return smem <= 220 * 1024;
+}
+
+bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name) {
+    (void)sm_count;
+    if (p.C != 3) return false;
+    if (p.radius < 1 || p.radius > 64) return false;
+    if (p.sw_margin_y < 3 || p.sw_margin_x < 2) return false;
+    if (!(p.NG == 0 || p.NG == 3 || p.NG == 6 || p.NG == 7)) return false;
+    if (p.padX < p.radius || (p.padX & 1) || (p.rec_pitch & 1)) return false;
+    StreamGeom g;
+    size_t smem = 0;
+    if (!stream_geometry(p, 4, g, smem)) return false;
+    if (name) *name = "stream";
+    return true;
+}
+
+int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *d_rowrange, int py,
+                             const char **name) {
+    StreamGeom g;
+    size_t smem = 0;
+    if (!stream_geometry(p, py, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: geometry not supported");
+    g.rowrange = d_rowrange;
+    const int grid = (int)std::min<long long>(g.total_tiles, 2LL * ctx->sm_count);
+    static thread_local char nm[64];
+    snprintf(nm, sizeof(nm), "stream<NG=%d,PY=%d,%s,D=%d>", p.NG, py, p.mode ? "moon" : "welch", g.depth);
+    if (name) *name = nm;
+#define SMC_STREAM_CASE(NGv)                                                                                          \
+    case NGv:                                                                                                         \
+        if (py == 4) {                                                                                                \
+            return p.mode == 0 ? launch<NGv, 4, 0>(ctx, p, g, grid, smem) : launch<NGv, 4, 1>(ctx, p, g, grid, smem); \
+        } else {                                                                                                      \
+            return p.mode == 0 ? launch<NGv, 2, 0>(ctx, p, g, grid, smem) : launch<NGv, 2, 1>(ctx, p, g, grid, smem); \
+        }
+    switch (p.NG) {
+        SMC_STREAM_CASE(0)
+        SMC_STREAM_CASE(3)
+        SMC_STREAM_CASE(6)
+        SMC_STREAM_CASE(7)
+        default: break;
+    }
+#undef SMC_STREAM_CASE
+    SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: NG=%d not instantiated", p.NG);
+}

@@ -1,0 +1,143 @@
+// smc_internal.h -- shared declarations of libstatmc_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/statmc_b200.h"
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void smc_set_error(const char *fmt, ...);
+
+#define SMC_FAIL(code, ...)         \
+    do {                            \
+        smc_set_error(__VA_ARGS__); \
+        return (code);              \
+    } while (0)
+
+#define SMC_CUDA(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            smc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);      \
+            return e__ == cudaErrorMemoryAllocation ? SMC_ERR_NOMEM : SMC_ERR_CUDA;                          \
+        }                                                                                                    \
+    } while (0)
+
+#define SMC_CHECK_LAUNCH(ctx)                                                                                \
+    do {                                                                                                     \
+        (ctx)->launches++;                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                                \
+        if (e__ != cudaSuccess) {                                                                            \
+            smc_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__);  \
+            return SMC_ERR_CUDA;                                                                             \
+        }                                                                                                    \
+    } while (0)
+
+// ---- plane descriptor as it sits in device tables: layout-compatible with cv::cuda::PtrStepSzb ----------
+// (src/ext/opencv/modules/core/include/opencv2/core/cuda_types.hpp:103-135: {T* data; size_t step; int cols; int rows;})
+struct SmcPtrStepSz {
+    unsigned char *data;
+    size_t step;
+    int cols;
+    int rows;
+};
+static_assert(sizeof(SmcPtrStepSz) == 24, "must match cv::cuda::PtrStepSzb");
+
+// ---- packed per-pixel record (64 B) -----------------------------------------------------------------------
+// float slots:  0 m.x  1 m.y  2 d.x  3 d.y | 4 m.z  5 d.z  6 V.z  7 g6 | 8 V.x  9 V.y 10 g0 11 g1 | 12 g2 13 g3 14 g4 15 g5
+//   m = Johnson-corrected mean (Welch mode) or raw mean (Moon mode); d = discriminator (Welch) or CI half-width (Moon)
+//   V = value to average (film or film-mean); g* = G-buffer channels pre-scaled by sqrt(-drFactor * log2(e))
+//   channels == 1: m -> slot 0, d -> slot 2, scalar value -> slot 4, film RGB (denoiseFilm, image 0) -> slots 8, 9, 6
+// Records are stored two to a 144-byte "line": 2 x 64 B + 16 B of padding.  The odd line stride makes eight
+// consecutive lines start in eight different 16-byte bank groups, so when the lanes of a warp read records that are
+// two apart (the streaming filter's mapping) every LDS.128 is bank-conflict-free, and -- unlike an XOR swizzle --
+// the chunk addresses of a record stay an affine function of its index: no per-load integer math in the inner loop.
+// A record row is laid out identically in HBM and in shared memory, so a row segment moves with one bulk copy.
+#define SMC_REC_FLOATS 16
+#define SMC_REC_BYTES 64
+#define SMC_LINE_BYTES 144
+static const int kGSlot[7] = {10, 11, 12, 13, 14, 15, 7};
+
+__host__ __device__ inline uint32_t smc_rec_offset(uint32_t pcol) {
+    // byte offset, within a record row, of the record at padded column `pcol`
+    return (pcol >> 1) * SMC_LINE_BYTES + (pcol & 1u) * SMC_REC_BYTES;
+}
+__host__ __device__ inline uint32_t smc_rec_chunk_offset(uint32_t pcol, uint32_t chunk) {
+    return smc_rec_offset(pcol) + chunk * 16u;
+}
+// bytes of a record row of `rec_pitch` records (rec_pitch is even)
+__host__ __device__ inline size_t smc_rec_row_bytes(int rec_pitch) { return (size_t)(rec_pitch / 2) * SMC_LINE_BYTES; }
+
+struct smc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    double alpha = 0.005;
+    float h_lut[SMC_T_LUT_ENTRIES];
+    float *d_lut = nullptr;  // device copy of the active table
+    // scratch plan cached for smc_filter_device_tables
+    struct smc_denoiser *cached = nullptr;
+    std::vector<unsigned char> cached_key;
+};
+
+struct smc_buffer {
+    smc_context *ctx;
+    void *dev;
+    size_t step;
+    int rows, cols, channels, dtype;
+    size_t elem_bytes;  // bytes per pixel
+};
+
+// filter parameters shared by the kernels (passed by value)
+struct SmcFilterParams {
+    int W, H;              // local plane size
+    int C;                 // 1 or 3
+    int NG;                // flattened G-buffer channels (0..7)
+    int radius;
+    int mode;              // smc_membership
+    int ptr_count;
+    int denoise_film;
+    int row_begin, row_end;
+    int padX;              // record columns left of x = 0
+    int rec_pitch;         // records per record row
+    size_t rec_image_stride;  // bytes between images
+    const unsigned char *rec; // record array base (image 0, record row 0 = y = -radius)
+    const float *sw;       // spatial table: (2r + 2*SW_MARGIN_Y) rows x sw_stride floats; -inf where invalid
+    int sw_stride, sw_margin_y, sw_margin_x;
+    const SmcPtrStepSz *out_ptrs;  // film_filtered_ptrs table (device)
+    SmcPtrStepSz film_filtered;    // "film-f"
+    const SmcPtrStepSz *accepted;  // optional, may be null
+};
+
+struct SmcPrepassParams {
+    int W, H, C, ptr_count, radius, mode, denoise_film;
+    int padX, rec_pitch;
+    size_t rec_image_stride;
+    unsigned char *rec;
+    int skip_top, skip_bottom;  // halo rows filled externally
+    const SmcPtrStepSz *n, *mean, *m2, *m3, *film_ptrs;
+    SmcPtrStepSz film;
+    int n_gbufs;
+    const SmcPtrStepSz *gbufs;
+    const unsigned char *gbuf_channels;  // device
+    const float *gbuf_dr_factors;        // device
+    const SmcPtrStepSz *mean_corr, *disc;  // optional tables (device) or null
+    const float *lut;
+};
+
+int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p);
+int smc_launch_filter_generic(smc_context *ctx, const SmcFilterParams &p);
+// returns SMC_ERR_UNSUPPORTED when the configuration has no streaming instantiation.
+// rowrange: device array, one {jlo, jhi} per spatial-table row; py: output rows per thread (2 or 4)
+int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *rowrange, int py,
+                             const char **name);
+bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name);
+#define SMC_SW_MARGIN_Y 3
+#define SMC_SW_MARGIN_X 2

@@ -1,0 +1,231 @@
+"""Parity of the CUDA denoiser (through the C ABI) against the oracle and against the reference's own CUDA kernels.
+
+Criteria (BASELINE.json / SURVEY.md 8d):
+  * mean-corr / discriminator planes: BIT-EXACT vs the float32 oracle and vs the reference kernels;
+  * membership: accepted-tap count per pixel IDENTICAL to the oracle (no flipped decisions);
+  * denoised film: relative mean-absolute difference <= 1e-4 vs the float64 transcription and vs the reference
+    CUDA kernel (max-abs reported); observed values are ~1e-7.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from statmc_b200 import _capi as capi
+from statmc_b200 import synth
+from statmc_b200.api import Buffer, Denoiser, denoise_host
+from util import bits_equal, max_abs, rel_mad, small_buffers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # relative MAD, stated tolerance of the north star
+
+
+def _check(ctx, b, radius, sd, kernel, **kw):
+    ours = denoise_host(ctx, b, radius=radius, sd=sd, kernel=kernel, want_aux=True, **kw)
+    ora = po.denoise(b, radius=radius, sd=sd, precision="f64", want_aux=True,
+                     gbuf_names=kw.get("gbuf_names", ("normal", "albedo")),
+                     gbuf_sds=tuple({"normal": 0.1, "albedo": 0.02, "depth": 1.0}[k]
+                                    for k in kw.get("gbuf_names", ("normal", "albedo"))))
+    assert bits_equal(ours["mean_corr"], ora["mean_corr"])
+    assert bits_equal(ours["disc"], ora["disc"])
+    assert np.array_equal(ours["accepted"], ora["accepted"]), "membership decisions differ from the oracle"
+    rm, ma = rel_mad(ours["film_f"], ora["film_f"]), max_abs(ours["film_f"], ora["film_f"])
+    print("kernel=%s r=%d relMAD=%.3e maxabs=%.3e" % (ours["kernel"], radius, rm, ma))
+    assert rm <= TOL
+    return ours, ora
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("W,H,radius,sd", [(96, 64, 5, 3.0), (300, 37, 20, 10.0), (257, 19, 7, 4.0), (40, 30, 12, 6.0)])
+def test_rgb_default_vs_oracle(ctx, kernel, W, H, radius, sd):
+    b = synth.moment_buffers(W, H, n=32, config_id=21)
+    ours, _ = _check(ctx, b, radius, sd, kernel)
+    assert ("stream" in ours["kernel"]) == (kernel == 2)
+
+
+def test_stream_and_generic_are_bit_identical(ctx):
+    b = synth.moment_buffers(520, 45, n=16, config_id=22, vary_n=True)
+    g = denoise_host(ctx, b, radius=9, sd=4.0, kernel=1)
+    s = denoise_host(ctx, b, radius=9, sd=4.0, kernel=2)
+    assert "generic" in g["kernel"] and "stream" in s["kernel"]
+    assert bits_equal(g["film_f"], s["film_f"])
+
+
+def test_varying_n_hits_lut_clamp(ctx):
+    b = small_buffers(128, 48, vary_n=True)  # n up to 4096 -> index 2n-3 clamps to 1023 (stat_denoiser.cu:200-202)
+    assert b["n"].max() > 513
+    _check(ctx, b, 6, 3.0, 0)
+
+
+def test_nan_pixels_pass_through(ctx):
+    b = small_buffers(64, 40)
+    b["n"][7, 9] = 1
+    b["m2"][7, 9] = 0
+    b["n"][0, 0] = 1
+    b["m2"][0, 0] = 0
+    for kernel in (1, 2):
+        ours = denoise_host(ctx, b, radius=5, sd=3.0, kernel=kernel, want_aux=True)
+        ora = po.denoise(b, radius=5, sd=3.0, precision="f64", want_aux=True)
+        assert np.array_equal(ours["accepted"], ora["accepted"])
+        assert ours["accepted"][7, 9] == 1 and bits_equal(ours["film_f"][7, 9], b["film"][7, 9])
+        assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
+
+
+@pytest.mark.parametrize("names", [(), ("normal",), ("normal", "albedo", "depth"), ("depth",), ("depth", "albedo")])
+def test_gbuffer_sets(ctx, names):
+    # scalar G-buffers (depth) work in the kernel but are broken on the reference's host side
+    b = small_buffers(80, 33)
+    _check(ctx, b, 6, 3.0, 0, gbuf_names=names)
+
+
+def test_tiny_and_degenerate_shapes(ctx):
+    for W, H, r in ((1, 1, 3), (3, 2, 8), (17, 1, 4), (1, 23, 4), (5, 5, 1)):
+        b = synth.moment_buffers(W, H, n=8, config_id=23)
+        for kernel in (1, 2):
+            ours = denoise_host(ctx, b, radius=r, sd=2.0, kernel=kernel, want_aux=True)
+            ora = po.denoise(b, radius=r, sd=2.0, precision="f64", want_aux=True)
+            assert np.array_equal(ours["accepted"], ora["accepted"]), (W, H, r, kernel)
+            assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
+
+
+def test_large_radius_generic(ctx):
+    b = synth.moment_buffers(90, 70, n=64, config_id=24)
+    ours = denoise_host(ctx, b, radius=70, sd=30.0, want_aux=True)
+    assert "generic" in ours["kernel"]
+    ora = po.denoise(b, radius=70, sd=30.0, precision="f64", want_aux=True)
+    assert np.array_equal(ours["accepted"], ora["accepted"])
+    assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
+
+
+def test_moon_membership(ctx):
+    b = small_buffers(100, 40)
+    ctx.set_alpha(0.002)  # Moon's 99.8 % table (README.md:149, stat_denoiser.cu:54-55)
+    try:
+        lut = po.t_table(0.002)
+        assert np.array_equal(ctx.t_table(), lut)
+        for kernel in (1, 2):
+            ours = denoise_host(ctx, b, radius=6, sd=3.0, kernel=kernel, membership=capi.SMC_MEMBER_MOON,
+                                want_aux=True)
+            ora = po.denoise(b, radius=6, sd=3.0, precision="f64", mode=1, lut=lut, want_aux=True)
+            assert np.array_equal(ours["accepted"], ora["accepted"])
+            assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
+    finally:
+        ctx.set_alpha(0.005)
+
+
+def test_scalar_statistics_and_dual_output(ctx):
+    # filter<float> with denoiseFilm && z == 0 filters both filmPtrs[0] and the RGB film (stat_denoiser.cu:251-273);
+    # a second image (z = 1) only its own plane.
+    W, H, r, sd = 70, 31, 5, 3.0
+    b = small_buffers(W, H)
+    b2 = synth.moment_buffers(W, H, n=24, config_id=31)
+    lum = lambda a: np.ascontiguousarray(a[..., 1])
+    planes = {}
+    for tag, src in (("a", b), ("b", b2)):
+        planes[tag] = {k: Buffer.from_array(ctx, lum(src[k])) for k in ("mean", "m2", "m3")}
+        planes[tag]["n"] = Buffer.from_array(ctx, src["n"])
+        planes[tag]["val"] = Buffer.from_array(ctx, lum(src["film"]))
+        planes[tag]["out"] = Buffer(ctx, H, W, 1)
+    film = Buffer.from_array(ctx, b["film"])
+    film_f = Buffer(ctx, H, W, 3)
+    g = [Buffer.from_array(ctx, b["normal"]), Buffer.from_array(ctx, b["albedo"])]
+    f = [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2]
+    dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2,
+                  n=[planes["a"]["n"], planes["b"]["n"]], mean=[planes["a"]["mean"], planes["b"]["mean"]],
+                  m2=[planes["a"]["m2"], planes["b"]["m2"]], m3=[planes["a"]["m3"], planes["b"]["m3"]],
+                  film_ptrs=[planes["a"]["val"], planes["b"]["val"]], film=film, gbufs=g, gbuf_dr_factors=f,
+                  film_filtered_ptrs=[planes["a"]["out"], planes["b"]["out"]], film_filtered=film_f,
+                  denoise_film=True)
+    dn.run()
+    ctx.synchronize()
+    for tag, src in (("a", b), ("b", b2)):
+        mc, dc = po.prepass(src["n"], lum(src["mean"]), lum(src["m2"]), lum(src["m3"]))
+        ref = po.filter(lum(src["film"]), [b["normal"], b["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
+                        precision="f64")
+        assert rel_mad(planes[tag]["out"].download(), ref) <= TOL
+        if tag == "a":
+            ref3 = po.filter(b["film"], [b["normal"], b["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
+                             precision="f64")
+            assert rel_mad(film_f.download(), ref3) <= TOL
+
+
+def test_multi_image_rgb_routing(ctx):
+    # filter<float3>, ptrCount = 2, denoiseFilm: image 0 filters `film` into film-f and leaves filmFilteredPtrs[0]
+    # untouched (stat_denoiser.cu:319-344); image 1 filters filmPtrs[1] into filmFilteredPtrs[1].
+    W, H, r, sd = 300, 21, 6, 3.0
+    b0, b1 = synth.moment_buffers(W, H, n=16, config_id=41), synth.moment_buffers(W, H, n=48, config_id=42)
+    up = lambda a: Buffer.from_array(ctx, a)
+    dev = [{k: up(s[k]) for k in ("n", "mean", "m2", "m3")} for s in (b0, b1)]
+    film_mean = [up(b0["film"] * 0 + 7), up(b1["film"])]
+    outs = [Buffer(ctx, H, W, 3), Buffer(ctx, H, W, 3)]
+    film, film_f = up(b0["film"]), Buffer(ctx, H, W, 3)
+    g = [up(b0["normal"]), up(b0["albedo"])]
+    f = [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2]
+    for kernel in (1, 2):
+        for o in outs:
+            o.zero()
+        dn = Denoiser(ctx, channels=3, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2,
+                      n=[d["n"] for d in dev], mean=[d["mean"] for d in dev], m2=[d["m2"] for d in dev],
+                      m3=[d["m3"] for d in dev], film_ptrs=film_mean, film=film, gbufs=g, gbuf_dr_factors=f,
+                      film_filtered_ptrs=outs, film_filtered=film_f, denoise_film=True, kernel=kernel)
+        dn.run()
+        ctx.synchronize()
+        assert not outs[0].download().any()
+        e0 = po.denoise(b0, radius=r, sd=sd, precision="f64")
+        assert rel_mad(film_f.download(), e0) <= TOL
+        mc, dc = po.prepass(b1["n"], b1["mean"], b1["m2"], b1["m3"])
+        e1 = po.filter(b1["film"], [b0["normal"], b0["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
+                       precision="f64")
+        assert rel_mad(outs[1].download(), e1) <= TOL
+        dn.close()
+
+
+def test_row_band_sharding_is_exact(ctx):
+    # a band carrying >= r halo rows above and >= r-1 below reproduces the rows of the unsharded run bit for bit
+    W, H, r, sd = 280, 90, 8, 4.0
+    b = synth.moment_buffers(W, H, n=32, config_id=51)
+    full = denoise_host(ctx, b, radius=r, sd=sd, kernel=2)["film_f"]
+    G = 3
+    for gidx in range(G):
+        y0, y1 = gidx * H // G, (gidx + 1) * H // G
+        lo, hi = max(0, y0 - r), min(H, y1 + r)
+        band = {k: np.ascontiguousarray(v[lo:hi]) for k, v in b.items()}
+        out = denoise_host(ctx, band, radius=r, sd=sd, kernel=2, row_begin=y0 - lo, row_end=y1 - lo)["film_f"]
+        assert bits_equal(out[y0 - lo:y1 - lo], full[y0:y1]), gidx
+    # and band generation itself is consistent with the full image
+    part = synth.moment_buffers(W, H // 3, n=32, config_id=51, row0=10, rows=H // 3, full_H=H)
+    assert bits_equal(part["mean"], b["mean"][10:10 + H // 3])
+
+
+def test_record_halo_exchange_mode(ctx):
+    # two "ranks" on one GPU: each holds only its own rows; prepass locally, swap record halos, filter
+    import ctypes as C
+    W, H, r, sd = 300, 64, 10, 5.0
+    b = synth.moment_buffers(W, H, n=32, config_id=52)
+    full = denoise_host(ctx, b, radius=r, sd=sd, kernel=2)["film_f"]
+    halves = []
+    for gidx in range(2):
+        y0, y1 = gidx * H // 2, (gidx + 1) * H // 2
+        part = {k: np.ascontiguousarray(v[y0:y1]) for k, v in b.items()}
+        dev = {k: Buffer.from_array(ctx, part[k]) for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
+        out = Buffer(ctx, y1 - y0, W, 3)
+        dn = Denoiser(ctx, channels=3, width=W, height=y1 - y0, radius=r, ds_factor=-0.5 / sd ** 2, n=[dev["n"]],
+                      mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]], film=dev["film"],
+                      gbufs=[dev["normal"], dev["albedo"]], gbuf_dr_factors=[-0.5 / 0.01, -0.5 / 0.0004],
+                      film_filtered_ptrs=[out], film_filtered=out, denoise_film=True, kernel=2,
+                      halo_top_external=(gidx == 1), halo_bottom_external=(gidx == 0))
+        dn.prepass()
+        halves.append((dn, out, dev))
+    ctx.synchronize()
+    # rank 0 bottom rows -> rank 1 top halo; rank 1 top rows -> rank 0 bottom halo (stream-ordered D2D copies)
+    def copy(src, dst):
+        (sp, sn), (dp, dnb) = src, dst
+        assert sn == dnb
+        capi.check(capi.lib.smc_memcpy_device(ctx.h, C.c_void_p(dp), C.c_void_p(sp), sn))
+
+    copy(halves[0][0].halo(0, 1), halves[1][0].halo(0, 2))
+    copy(halves[1][0].halo(0, 0), halves[0][0].halo(0, 3))
+    for dn, _, _ in halves:
+        dn.filter()
+    ctx.synchronize()
+    got = np.concatenate([halves[0][1].download(), halves[1][1].download()], axis=0)
+    assert bits_equal(got, full)

@@ -1,0 +1,125 @@
+"""Parity of the accumulation stage (smc_accumulate / smc_merge_moments / smc_calculate_mean_vars) with the oracle.
+
+north star: moments within 1e-6 relative error of the reference's CPU accumulation (fp32).  Stronger here: against the
+oracle run with sqrtf (the one deliberate deviation from the reference's powf(s, .5f)) every plane is BIT-EXACT;
+against the powf oracle the scale-aware relative error is <= 1e-6.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from statmc_b200 import synth
+from statmc_b200.api import Buffer, MomentState
+from util import bits_equal, moment_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _scale(state64):
+    """per-pixel scale n*sigma^k for the k-th central moment sum (k = 1 -> sigma itself for the mean)."""
+    n = np.maximum(state64["n"].astype(np.float64), 2)[..., None]
+    sigma = np.sqrt(np.maximum(state64["m2"], 1e-30) / n)
+    return {"mean": sigma, "m2": n * sigma ** 2, "m3": n * sigma ** 3,
+            "film_mean": np.sqrt(np.maximum(state64["film_m2"], 1e-30) / n), "film_m2": np.maximum(state64["film_m2"], 1e-30)}
+
+
+@pytest.mark.parametrize("heavy", [False, True])
+def test_transform_m3_stream_in_batches(ctx, heavy):
+    W, H = 67, 23
+    sc = synth.scene(W, H, 61)
+    st = MomentState(ctx, W, H, 3, transform=True)
+    exact = po.new_state(H, W)        # oracle with sqrtf: must match to the bit
+    ref = po.new_state(H, W)          # oracle with powf (reference semantics)
+    f64 = po.new_state(H, W, dtype=np.float64)
+    first = 0
+    for S in (4, 4, 8, 16, 32):       # the reference's 4 -> 8 -> 16 ... schedule (statpath.cpp:269-279)
+        x = synth.sample_stream(W, H, S, config_id=61, first_sample=first, heavy_tail=heavy, sc=sc)
+        first += S
+        st.add_samples(x)
+        po.accumulate(exact, x, transform=True, use_sqrt=True)
+        po.accumulate(ref, x, transform=True, use_sqrt=False)
+        po.accumulate_f64(f64, x, transform=True)
+        got = st.download()
+        assert np.array_equal(got["n"], exact["n"].astype(np.int32))
+        for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+            assert bits_equal(got[k], exact[k]), (k, first)
+        sc64 = _scale(f64)
+        for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+            e = moment_rel_err(got[k], ref[k], None, sc64[k])
+            assert e <= 1e-6, (k, first, e)
+
+
+@pytest.mark.parametrize("C,transform,mm", [(1, False, 1), (1, False, 2), (3, False, 1), (3, False, 3), (1, True, 3),
+                                            (3, True, 2), (3, True, 1)])
+def test_all_update_variants_bit_exact(ctx, C, transform, mm):
+    W, H, S = 41, 9, 11
+    rng = np.random.default_rng(C * 10 + mm)
+    x = rng.gamma(1.5, 1.0, size=(S, H, W, C)).astype(np.float32)
+    st = MomentState(ctx, W, H, C, transform=transform)
+    st.add_samples(x, max_moment=mm)
+    st.add_samples(x[::-1].copy(), max_moment=mm)
+    o = po.new_state(H, W, C)
+    po.accumulate(o, x, transform=transform, max_moment=mm, use_sqrt=True)
+    po.accumulate(o, x[::-1].copy(), transform=transform, max_moment=mm, use_sqrt=True)
+    got = st.download()
+    sq = (lambda a: a[..., 0]) if C == 1 else (lambda a: a)
+    assert np.array_equal(got["n"], o["n"].astype(np.int32))
+    for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+        assert bits_equal(got[k], sq(o[k])), k
+
+
+def test_row_range_update(ctx):
+    W, H, S = 33, 12, 5
+    x = np.random.default_rng(3).random((S, 4, W, 3), dtype=np.float32)
+    st = MomentState(ctx, W, H, 3, transform=True)
+    tmp = Buffer(ctx, 1, x.size, 1)
+    tmp.upload(x.reshape(1, -1))
+    from statmc_b200._capi import lib
+    st.add_samples_dev(lib.smc_buffer_dev(tmp.h), S, 3, 5, 9)
+    ctx.synchronize()
+    got = st.download()
+    assert np.all(got["n"][5:9] == S) and not got["n"][:5].any() and not got["n"][9:].any()
+    o = po.new_state(4, W)
+    po.accumulate(o, x, transform=True, use_sqrt=True)
+    assert bits_equal(got["m3"][5:9], o["m3"])
+
+
+def test_pairwise_merge_matches_sequential(ctx):
+    # new capability (no reference counterpart): Chan/Pebay merge of two independently accumulated halves
+    W, H = 50, 14
+    sc = synth.scene(W, H, 62)
+    xa = synth.sample_stream(W, H, 24, config_id=62, first_sample=0, sc=sc)
+    xb = synth.sample_stream(W, H, 40, config_id=62, first_sample=24, sc=sc)
+    a, b = MomentState(ctx, W, H), MomentState(ctx, W, H)
+    a.add_samples(xa)
+    b.add_samples(xb)
+    a.merge(b)
+    ctx.synchronize()
+    got = a.download()
+    seq = po.new_state(H, W, dtype=np.float64)
+    po.accumulate_f64(seq, np.concatenate([xa, xb]), transform=True)
+    sc64 = _scale(seq)
+    assert np.all(got["n"] == 64)
+    for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+        assert moment_rel_err(got[k], seq[k], None, sc64[k]) < 2e-5, k
+    # merging an empty set is the identity; merging into an empty set copies
+    e = MomentState(ctx, W, H)
+    before = a.download()
+    a.merge(e)
+    e.merge(a)
+    ctx.synchronize()
+    after, copied = a.download(), e.download()
+    for k in before:
+        assert bits_equal(before[k], after[k]) and np.allclose(copied[k], before[k], rtol=1e-6), k
+
+
+def test_calculate_mean_vars(ctx):
+    W, H = 45, 8
+    b = synth.moment_buffers(W, H, n=16, config_id=63, vary_n=True)
+    st = MomentState(ctx, W, H)
+    st.n.upload(b["n"])
+    st.film_m2.upload(b["film_m2"])
+    out = Buffer(ctx, H, W, 3)
+    st.calculate_mean_vars(out)
+    ctx.synchronize()
+    assert bits_equal(out.download(), po.calculate_mean_vars(b["n"], b["film_m2"]))

@@ -1,0 +1,171 @@
+"""CPU-side pins of the oracle (oracle/statmc_oracle.c) -- no GPU needed.
+
+The reference has no tests or golden vectors for this path, so the pins are:
+  * its t-quantile table text (hash committed in tests/golden/t_quantiles.json by tools/gen_t_quantiles.py, which
+    parsed stat_denoiser.cu:53-63 in the build container);
+  * outputs of the reference's own CUDA kernels on seeded inputs, captured on a B200 by tools/make_golden_ref.py and
+    committed as tests/golden/ref_cuda_*.npz (checked in test_oracle_vs_reference_golden);
+  * closed-form properties of the algorithm the reference states (window tap counts, constant-image invariance,
+    exact moments of short streams).
+"""
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from statmc_b200 import synth
+from util import rel_mad, small_buffers
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<f4").tobytes()).hexdigest()
+
+
+def test_t_table_matches_reference_text():
+    g = json.load(open(os.path.join(GOLDEN, "t_quantiles.json")))
+    assert "reference_sha256" in g, "golden file was generated without /root/reference"
+    for name, alpha in g["alphas"].items():
+        assert _sha(po.t_table(alpha)) == g["reference_sha256"][name], name
+    t = po.t_table(0.005)
+    for i, v in g["spot_005"].items():
+        assert float(t[int(i)]) == v
+
+
+def test_window_tap_counts():
+    # #{(dy,dx) in [-r,r)^2 : dy^2+dx^2 <= r^2}
+    assert [po.taps_in_window(r) for r in (6, 10, 20, 32, 40)] == [111, 315, 1255, 3207, 5023]
+
+
+def test_accumulate_matches_exact_moments():
+    rng = np.random.default_rng(5)
+    S, H, W = 37, 5, 7
+    x = rng.gamma(2.0, 1.0, size=(S, H, W, 3)).astype(np.float32)
+    st = po.new_state(H, W)
+    po.accumulate(st, x, transform=False, max_moment=3)
+    xd = x.astype(np.float64)
+    mean = xd.mean(0)
+    m2 = ((xd - mean) ** 2).sum(0)
+    m3 = ((xd - mean) ** 3).sum(0)
+    assert np.all(st["n"] == S)
+    np.testing.assert_allclose(st["mean"], mean, rtol=2e-6)
+    np.testing.assert_allclose(st["m2"], m2, rtol=2e-5)
+    np.testing.assert_allclose(st["m3"], m3, rtol=1e-3, atol=1e-3 * np.abs(m3).max())
+    # AddSample copies mean/m2 to the film moments (estimator.h:209-210)
+    assert np.array_equal(st["film_mean"], st["mean"]) and np.array_equal(st["film_m2"], st["m2"])
+
+
+def test_accumulate_transform_and_batch_continuation():
+    rng = np.random.default_rng(6)
+    S, H, W = 24, 4, 6
+    x = rng.gamma(0.5, 2.0, size=(S, H, W, 3)).astype(np.float32)
+    a = po.new_state(H, W)
+    po.accumulate(a, x, transform=True)
+    b = po.new_state(H, W)  # 4, 4, 8, 8: the reference continues the same running state across iterations
+    for lo, hi in ((0, 4), (4, 8), (8, 16), (16, 24)):
+        po.accumulate(b, x[lo:hi], transform=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    bc = 2.0 * (np.sqrt(x.astype(np.float64)) - 1.0)
+    np.testing.assert_allclose(a["mean"], bc.mean(0), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(a["film_mean"], x.astype(np.float64).mean(0), rtol=1e-5)
+    np.testing.assert_allclose(a["film_m2"], ((x - x.mean(0)) ** 2).astype(np.float64).sum(0), rtol=1e-4)
+    # powf(s, .5f) vs sqrtf(s): at most an ulp apart per sample -> moments agree to ~1e-6
+    c = po.new_state(H, W)
+    po.accumulate(c, x, transform=True, use_sqrt=True)
+    np.testing.assert_allclose(c["mean"], a["mean"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(c["m2"], a["m2"], rtol=1e-5)
+
+
+def test_accumulate_moment_levels():
+    rng = np.random.default_rng(7)
+    x = rng.random((9, 3, 3, 1)).astype(np.float32)
+    s1, s2 = po.new_state(3, 3, 1), po.new_state(3, 3, 1)
+    po.accumulate(s1, x, transform=False, max_moment=1)
+    po.accumulate(s2, x, transform=False, max_moment=2)
+    assert np.array_equal(s1["mean"], s2["mean"]) and not s1["m2"].any() and s2["m2"].any() and not s2["m3"].any()
+
+
+def test_mean_vars_and_row_bug():
+    n = np.array([[4, 9], [16, 25]], dtype=np.int32)
+    m2 = np.arange(1, 13, dtype=np.float32).reshape(2, 2, 3)
+    ok = po.calculate_mean_vars(n, m2)
+    np.testing.assert_allclose(ok, m2 / (n * (n - 1.0))[..., None], rtol=1e-6)
+    bug = po.calculate_mean_vars(n, m2, per_row_n_bug=True)  # estimator.cpp:540: n read once per row
+    np.testing.assert_allclose(bug[:, 1], m2[:, 1] / (n[:, 0] * (n[:, 0] - 1.0))[:, None], rtol=1e-6)
+
+
+def test_prepass_formulas():
+    b = small_buffers(vary_n=True)
+    mc, dc = po.prepass(b["n"], b["mean"], b["m2"], b["m3"])
+    n = b["n"].astype(np.float64)[..., None]
+    s2 = b["m2"] / (n - 1)
+    corr = np.where(s2 > np.finfo(np.float32).eps, (b["m3"] / n) / (6 * s2 * n), 0)
+    np.testing.assert_allclose(mc, b["mean"] + corr, rtol=2e-6, atol=1e-6)
+    t = po.t_table()[np.minimum(2 * b["n"] - 3, 1023)][..., None].astype(np.float64)
+    disc = (b["mean"] + corr) ** 2 - t * t * b["m2"] / (n * (n - 1))
+    np.testing.assert_allclose(dc, disc, rtol=1e-4, atol=1e-4)
+
+
+def test_filter_constant_image_and_counts():
+    H, W, r = 20, 24, 4
+    b = small_buffers(W, H)
+    for k in ("mean", "m2", "m3", "film", "normal", "albedo"):
+        b[k][...] = b[k][0, 0]
+    res = po.denoise(b, radius=r, sd=2.0, want_aux=True)
+    np.testing.assert_allclose(res["film_f"], b["film"], rtol=1e-6)
+    # identical pixels: every tap of the window is accepted, also at the replicated borders
+    assert np.all(res["accepted"] == po.taps_in_window(r))
+
+
+def test_filter_half_open_window_and_clamp():
+    # one very bright pixel far from everything else statistically: only its own centre tap accepts it,
+    # so the output equals the input there; the impulse response of the *weights* shows the [c-r, c+r) window.
+    H, W, r = 15, 15, 3
+    z = np.zeros((H, W, 3), np.float32)
+    mc = z + 1.0
+    disc = z - 1.0          # disc_C + disc_I = -2 <= 2*1*1: everything is a member
+    film = z.copy()
+    film[7, 7] = 1.0
+    out, acc = po.filter(film, [], [], r, -0.5 / 4.0, mean_corr=mc, disc=disc, want_accepted=True)
+    nz = np.argwhere(out[..., 0] > 0)
+    # pixel (y,x) sees the impulse iff 7 - y in [-r, r) and 7 - x in [-r, r) and inside the disc
+    assert nz[:, 0].min() == 7 - (r - 1) and nz[:, 0].max() == 7 + r
+    assert nz[:, 1].min() == 7 - (r - 1) and nz[:, 1].max() == 7 + r
+    assert acc[7, 7] == po.taps_in_window(r) and acc[0, 0] == po.taps_in_window(r)  # clamped taps still count
+
+
+def test_filter_f32_vs_f64_transcription():
+    b = small_buffers()
+    a = po.denoise(b, radius=6, sd=3.0, precision="f32")
+    d = po.denoise(b, radius=6, sd=3.0, precision="f64")
+    assert rel_mad(a, d) < 1e-6
+
+
+def test_nan_statistics_pass_through():
+    b = small_buffers(40, 30)
+    b["n"][10, 12] = 1  # n = 1: s2 = m2/0 -> the pixel is excluded everywhere and passes through
+    b["m2"][10, 12] = 0
+    res = po.denoise(b, radius=4, sd=2.0, want_aux=True)
+    assert res["accepted"][10, 12] == 1
+    np.testing.assert_array_equal(res["film_f"][10, 12], b["film"][10, 12])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_cuda_*.npz"))) or [None])
+def test_oracle_vs_reference_golden(path):
+    if path is None:
+        pytest.skip("no reference-CUDA golden fixtures committed yet (tools/make_golden_ref.py, needs the GPU box)")
+    g = np.load(path)
+    cfg = json.loads(str(g["config"]))
+    b = synth.moment_buffers(cfg["W"], cfg["H"], n=cfg["n"], config_id=cfg["config_id"], vary_n=cfg["vary_n"])
+    res = po.denoise(b, radius=cfg["radius"], sd=cfg["sd"], gbuf_sds=(cfg["normal_sd"], cfg["albedo_sd"]),
+                     want_aux=True)
+    # prepass planes: bit-exact against the reference kernels' output
+    assert np.array_equal(res["mean_corr"].view(np.uint32), g["mean_corr"].view(np.uint32))
+    assert np.array_equal(res["disc"].view(np.uint32), g["disc"].view(np.uint32))
+    assert rel_mad(res["film_f"], g["film_f"]) < 1e-5
