@@ -89,10 +89,6 @@ class RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def band_of(rank: int, world: int, H: int):
-    return rank * H // world, (rank + 1) * H // world
-
-
 def cpu_baseline(W, radius, sd, n, seconds_target=12.0):
     """The oracle port (CPU restatement of the reference kernels, OpenMP over all host cores) on a bounded sample:
     a full-width band of rows of the same workload.  Reported as baseline only."""
@@ -129,6 +125,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 streaming")
     ap.add_argument("--halo", default="exchange", choices=["exchange", "redundant"],
                     help="N>1: exchange record halos over NVLink (NCCL send/recv) or carry raw halo rows per band")
+    ap.add_argument("--gbufs", type=int, default=2, help="experiments: 0 = no G-buffers, 1 = normal only, 2 = normal + albedo")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-accum", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -152,8 +149,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from statmc_b200 import synth
-    from statmc_b200._capi import lib
+    from statmc_b200 import sharding, synth
     from statmc_b200.api import Buffer, Context, Denoiser, MomentState, PinnedArray
 
     W, H, radius, sd, n = WORKLOADS[args.workload]
@@ -164,12 +160,13 @@ def main():
     ctx = Context(local, stream=stream)
 
     # ---- this rank's band ------------------------------------------------------------------------------------
-    y0, y1 = band_of(rank, world, H)
+    y0, y1 = sharding.band_of(rank, world, H)
     exchange = world > 1 and args.halo == "exchange"
     if exchange:
+        sharding.check_exchangeable(world, H, radius)
         lo, hi = y0, y1                                   # own rows only; record halos come from the neighbours
     else:
-        lo, hi = max(0, y0 - radius), min(H, y1 + radius)  # raw halo rows carried, prepass recomputed on them
+        lo, hi, _, _ = sharding.band_with_raw_halo(rank, world, H, radius)  # raw halo rows, prepass recomputed on them
     rows = hi - lo
     bufs = synth.moment_buffers(W, H, n=n, config_id=3, row0=lo, rows=rows, full_H=H)
     names = ("n", "mean", "m2", "m3", "film", "normal", "albedo")
@@ -181,8 +178,8 @@ def main():
     out_host = PinnedArray((y1 - y0, W, 3), np.float32)
     dn = Denoiser(ctx, channels=3, width=W, height=rows, radius=radius, ds_factor=-0.5 / (sd * sd),
                   n=[dev["n"]], mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]],
-                  film=dev["film"], gbufs=[dev["normal"], dev["albedo"]],
-                  gbuf_dr_factors=[-0.5 / NORMAL_SD ** 2, -0.5 / ALBEDO_SD ** 2], film_filtered_ptrs=[out],
+                  film=dev["film"], gbufs=[dev["normal"], dev["albedo"]][:args.gbufs],
+                  gbuf_dr_factors=[-0.5 / NORMAL_SD ** 2, -0.5 / ALBEDO_SD ** 2][:args.gbufs], film_filtered_ptrs=[out],
                   film_filtered=out, denoise_film=True, row_begin=y0 - lo, row_end=y1 - lo, kernel=args.kernel,
                   halo_top_external=exchange and rank > 0, halo_bottom_external=exchange and rank < world - 1)
 
@@ -197,13 +194,7 @@ def main():
             halo_t[which] = torch.as_tensor(RawCuda(p, nb), device=torch.device("cuda", local))
 
     def exchange_halos():
-        ops = []
-        if rank > 0:
-            ops += [dist.P2POp(dist.isend, halo_t[0], rank - 1), dist.P2POp(dist.irecv, halo_t[2], rank - 1)]
-        if rank < world - 1:
-            ops += [dist.P2POp(dist.isend, halo_t[1], rank + 1), dist.P2POp(dist.irecv, halo_t[3], rank + 1)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+        sharding.exchange_halos(dist, rank, world, halo_t[0], halo_t[1], halo_t[2], halo_t[3])
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     filt_ms, pre_ms = [], []

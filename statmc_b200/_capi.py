@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstatmc_b200.so")
+_VARIANT = os.environ.get("SMC_LIB_VARIANT", "")  # experiment builds only (statmc_b200/build.py --variant)
+LIB_PATH = os.path.join(_HERE, "libstatmc_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 SMC_OK, SMC_ERR_INVALID, SMC_ERR_CUDA, SMC_ERR_NOMEM, SMC_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SMC_F32, SMC_I32 = 0, 1

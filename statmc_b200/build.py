@@ -71,9 +71,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment builds: statmc_b200/libstatmc_b200_<name>.so compiled with extra -D flags (A/B timing only;
+    select with the environment variable SMC_LIB_VARIANT=<name>)."""
+    global OBJ, LIB, NVCC_FLAGS
+    saved = (OBJ, LIB, list(NVCC_FLAGS))
+    try:
+        OBJ = os.path.join(ROOT, "build", "obj_" + name)
+        LIB = os.path.join(ROOT, "statmc_b200", "libstatmc_b200_%s.so" % name)
+        NVCC_FLAGS = NVCC_FLAGS + ["-D" + d for d in defines]
+        return build_library(force=False)
+    finally:
+        OBJ, LIB, NVCC_FLAGS = saved[0], saved[1], saved[2]
+
+
 def main() -> None:
     force = "--force" in sys.argv
     verbose = "-v" in sys.argv
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        return
     print(build_library(force, verbose))
 
 

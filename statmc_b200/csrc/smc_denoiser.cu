@@ -109,8 +109,11 @@ static int select_kernel(smc_denoiser *d) {
         SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming kernel requested but not available for C=%d NG=%d r=%d", d->C, d->NG,
                  d->radius);
     d->use_stream = ok && d->kernel_pref != 1;
-    d->py = 4;
-    if (const char *e = getenv("SMC_STREAM_PY")) d->py = atoi(e) == 2 ? 2 : 4;
+    // output rows per thread: 2 x 2 pixels per thread wastes less work at the rim of the window (x1.06 at r = 20,
+    // x1.23 at r = 6, against x1.13 / x1.46 for 2 x 4) and leaves room for 3 CTAs per SM; measured faster at every
+    // radius tried (profiles/r1_variants.md).  SMC_STREAM_PY=4 selects the 2 x 4 variant for experiments.
+    d->py = 2;
+    if (const char *e = getenv("SMC_STREAM_PY")) d->py = atoi(e) == 4 ? 4 : 2;
     snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", d->use_stream ? "stream" : "generic");
     return SMC_OK;
 }

@@ -10,27 +10,47 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ float smc_ex2(float x) {
+#ifdef SMC_EXPERIMENT_NO_MUFU  // timing experiment only (wrong results): what the kernel costs without the SFU op
+    return x * 0.001f;
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
-// packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two IEEE-rounded lanes
+// Two-lane fp32 arithmetic.  Default: Blackwell packed FADD2 / FMUL2 / FFMA2 (one instruction, two IEEE-rounded
+// lanes).  -DSMC_SCALAR_MATH=1 builds the same arithmetic from scalar ops (bit-identical results) for A/B timing.
+#ifndef SMC_SCALAR_MATH
+#define SMC_SCALAR_MATH 0
+#endif
 __device__ __forceinline__ float2 smc_add2(float2 a, float2 b) {
+#if SMC_SCALAR_MATH
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+#else
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2 *>(&rd);
+#endif
 }
 __device__ __forceinline__ float2 smc_mul2(float2 a, float2 b) {
+#if SMC_SCALAR_MATH
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#else
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2 *>(&rd);
+#endif
 }
 __device__ __forceinline__ float2 smc_fma2(float2 a, float2 b, float2 c) {
+#if SMC_SCALAR_MATH
+    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+#else
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
                        rc = *reinterpret_cast<unsigned long long *>(&c), rd;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
+#endif
 }
 
 // What a thread keeps in registers about one centre pixel.
@@ -80,6 +100,9 @@ __device__ __forceinline__ void smc_make_centre(const SmcRec &r, SmcCentre<C, NG
 
 template <int C, int NG, int MODE>
 __device__ __forceinline__ bool smc_member(const SmcCentre<C, NG> &c, const SmcRec &r) {
+#ifdef SMC_EXPERIMENT_NO_MEMBER  // timing experiment only (wrong results)
+    return r.c0.x > -1e30f;
+#endif
     if (MODE == 0) {
         if (C == 3) {
             const float2 s = smc_add2(c.d01, make_float2(r.c0.z, r.c0.w));

@@ -15,6 +15,7 @@
 // is the FP32 pipe: see DESIGN.md.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "smc_filter_math.cuh"
 #include "smc_internal.h"
@@ -24,6 +25,9 @@ namespace {
 constexpr int kTileW = 256;
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
+#ifndef SMC_STREAM_MINB
+#define SMC_STREAM_MINB 2  // resident CTAs per SM the register allocation is bounded for
+#endif
 
 struct StreamGeom {
     int tiles_x, tiles_y;
@@ -134,7 +138,7 @@ __device__ __forceinline__ void seg_of(const SmcFilterParams &p, const TileCoord
 }
 
 template <int NG, int PY, int MODE, bool COUNT>
-__global__ void __launch_bounds__(kThreads, 2) filter_stream_kernel(const SmcFilterParams p, const StreamGeom g) {
+__global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kernel(const SmcFilterParams p, const StreamGeom g) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [ring: depth * slot_bytes][sw table: sw_rows * sw_stride floats][rowrange: sw_rows int2][barriers]
     unsigned char *ring = smem;
@@ -297,20 +301,24 @@ __global__ void __launch_bounds__(kThreads, 2) filter_stream_kernel(const SmcFil
     }
 }
 
-template <int NG, int PY, int MODE>
-int launch(smc_context *ctx, const SmcFilterParams &p, const StreamGeom &g, int grid, size_t smem) {
-    const bool count = p.accepted != nullptr;
-    if (count) {
-        auto k = filter_stream_kernel<NG, PY, MODE, true>;
-        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
-    } else {
-        auto k = filter_stream_kernel<NG, PY, MODE, false>;
-        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
-    }
+template <typename K>
+int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &g, size_t smem) {
+    SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem));
+    if (per_sm < 1) SMC_FAIL(SMC_ERR_CUDA, "streaming filter does not fit on an SM (smem %zu)", smem);
+    // persistent grid: one wave of resident CTAs, each walking tiles b, b + grid, ... (neighbouring tiles run
+    // concurrently, so the rows they share are fetched from HBM once and served from L2)
+    const int grid = (int)std::min<long long>(g.total_tiles, (long long)per_sm * ctx->sm_count);
+    k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
     SMC_CHECK_LAUNCH(ctx);
     return SMC_OK;
+}
+
+template <int NG, int PY, int MODE>
+int launch(smc_context *ctx, const SmcFilterParams &p, const StreamGeom &g, size_t smem) {
+    if (p.accepted != nullptr) return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, true>, p, g, smem);
+    return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, false>, p, g, smem);
 }
 
 }  // namespace
@@ -329,15 +337,26 @@ static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, siz
     g.slot_bytes = (((g.seg_max_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
     g.sw_rows = 2 * p.radius + 2 * p.sw_margin_y;
     const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 2 * 8 * 8 + 64;
-    // prefer 2 CTAs per SM (2 x (smem + 1 KB reserved) <= 227 KB), ring depth 4 then 3
+    // Ring depth / residency (measured on B200, 4K r=20, profiles/r1_variants.md): 3 CTAs per SM with a 3-deep ring
+    // beat 2 CTAs with 4 slots when PY = 2 (166 registers per thread allow 3 CTAs); PY = 4 (250 registers) is limited to
+    // 2 CTAs by the register file, where 4 slots fit.  Each CTA also reserves 1 KB of shared memory.
     smem = 0;
-    for (int depth = 4; depth >= 3; depth--) {
-        const size_t s = (size_t)depth * g.slot_bytes + fixed;
-        if (2 * (s + 1024) <= 227 * 1024 || depth == 3) {
-            g.depth = depth;
-            smem = s;
-            break;
-        }
+    int want = 0;
+    if (const char *e = getenv("SMC_STREAM_DEPTH")) want = atoi(e);  // tuning knob
+    const size_t s3 = 3 * (size_t)g.slot_bytes + fixed, s4 = 4 * (size_t)g.slot_bytes + fixed;
+    if (PY == 2 && 3 * (s3 + 1024) <= 227 * 1024) {
+        g.depth = 3;
+        smem = s3;
+    } else if (2 * (s4 + 1024) <= 227 * 1024) {
+        g.depth = 4;
+        smem = s4;
+    } else {
+        g.depth = 3;
+        smem = s3;
+    }
+    if (want >= 2 && want <= 8) {
+        g.depth = want;
+        smem = (size_t)want * g.slot_bytes + fixed;
     }
     return smem <= 220 * 1024;
 }
@@ -351,7 +370,7 @@ bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const c
     if (p.padX < p.radius || (p.padX & 1) || (p.rec_pitch & 1)) return false;
     StreamGeom g;
     size_t smem = 0;
-    if (!stream_geometry(p, 4, g, smem)) return false;
+    if (!stream_geometry(p, 2, g, smem) || !stream_geometry(p, 4, g, smem)) return false;
     if (name) *name = "stream";
     return true;
 }
@@ -362,16 +381,15 @@ int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const i
     size_t smem = 0;
     if (!stream_geometry(p, py, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: geometry not supported");
     g.rowrange = d_rowrange;
-    const int grid = (int)std::min<long long>(g.total_tiles, 2LL * ctx->sm_count);
     static thread_local char nm[64];
     snprintf(nm, sizeof(nm), "stream<NG=%d,PY=%d,%s,D=%d>", p.NG, py, p.mode ? "moon" : "welch", g.depth);
     if (name) *name = nm;
 #define SMC_STREAM_CASE(NGv)                                                                                          \
     case NGv:                                                                                                         \
         if (py == 4) {                                                                                                \
-            return p.mode == 0 ? launch<NGv, 4, 0>(ctx, p, g, grid, smem) : launch<NGv, 4, 1>(ctx, p, g, grid, smem); \
+            return p.mode == 0 ? launch<NGv, 4, 0>(ctx, p, g, smem) : launch<NGv, 4, 1>(ctx, p, g, smem); \
         } else {                                                                                                      \
-            return p.mode == 0 ? launch<NGv, 2, 0>(ctx, p, g, grid, smem) : launch<NGv, 2, 1>(ctx, p, g, grid, smem); \
+            return p.mode == 0 ? launch<NGv, 2, 0>(ctx, p, g, smem) : launch<NGv, 2, 1>(ctx, p, g, smem); \
         }
     switch (p.NG) {
         SMC_STREAM_CASE(0)

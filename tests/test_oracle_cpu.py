@@ -162,7 +162,7 @@ def test_oracle_vs_reference_golden(path):
         pytest.skip("no reference-CUDA golden fixtures committed yet (tools/make_golden_ref.py, needs the GPU box)")
     g = np.load(path)
     cfg = json.loads(str(g["config"]))
-    b = synth.moment_buffers(cfg["W"], cfg["H"], n=cfg["n"], config_id=cfg["config_id"], vary_n=cfg["vary_n"])
+    b = {k[3:]: g[k] for k in g.files if k.startswith("in_")}  # inputs travel with the fixture
     res = po.denoise(b, radius=cfg["radius"], sd=cfg["sd"], gbuf_sds=(cfg["normal_sd"], cfg["albedo_sd"]),
                      want_aux=True)
     # prepass planes: bit-exact against the reference kernels' output

@@ -3,8 +3,10 @@
 seeded synthetic inputs, as small golden fixtures for the CPU-side tests (tests/test_oracle_cpu.py).
 
 Run on the GPU box:   python tools/make_golden_ref.py gpurun_out/golden
-then copy gpurun_out/golden/ref_cuda_*.npz into tests/golden/ and commit them.  Inputs are regenerated from the
-seed by statmc_b200.synth, so only the outputs (mean-corr, discriminator, film-f) are stored, as float32.
+then copy gpurun_out/golden/ref_cuda_*.npz into tests/golden/ and commit them.  The fixtures are self-contained:
+inputs (n, mean, m2, m3, film, normal, albedo) AND the reference kernels' outputs (mean-corr, discriminator, film-f)
+are stored, because numpy's float32 sin/exp differ by an ulp between CPU generations and a regenerated input would
+not be bit-identical on another machine.
 """
 import json
 import os
@@ -17,9 +19,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CASES = [
-    dict(name="a", W=72, H=40, n=16, config_id=81, vary_n=False, radius=6, sd=3.0, normal_sd=0.1, albedo_sd=0.02),
-    dict(name="b", W=64, H=48, n=64, config_id=82, vary_n=True, radius=9, sd=5.0, normal_sd=0.1, albedo_sd=0.02),
-    dict(name="c", W=50, H=30, n=256, config_id=83, vary_n=False, radius=20, sd=10.0, normal_sd=0.1, albedo_sd=0.02),
+    dict(name="a", W=56, H=32, n=16, config_id=81, vary_n=False, radius=6, sd=3.0, normal_sd=0.1, albedo_sd=0.02),
+    dict(name="b", W=48, H=40, n=64, config_id=82, vary_n=True, radius=9, sd=5.0, normal_sd=0.1, albedo_sd=0.02),
+    dict(name="c", W=44, H=26, n=256, config_id=83, vary_n=False, radius=20, sd=10.0, normal_sd=0.1, albedo_sd=0.02),
 ]
 
 
@@ -36,7 +38,7 @@ def main():
         cfg = {k: v for k, v in c.items() if k != "name"}
         np.savez_compressed(os.path.join(out, "ref_cuda_%s.npz" % c["name"]), config=json.dumps(cfg),
                             mean_corr=r["mean_corr"], disc=r["disc"], film_f=r["film_f"],
-                            input_sha=np.frombuffer(b["mean"].tobytes()[:64], dtype=np.uint8))
+                            **{"in_" + k: b[k] for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")})
         print("wrote", c["name"], r["film_f"].shape, float(np.abs(r["film_f"]).mean()))
     ctx.close()
 
