@@ -208,6 +208,29 @@ int smc_denoiser_prepass(smc_denoiser *d);
 int smc_denoiser_filter(smc_denoiser *d);
 /* prepass + filter: the whole of cv::cuda::stat_denoiser::filter<T> */
 int smc_denoiser_run(smc_denoiser *d);
+/* Row-range forms (row-band pipelining; overlapping the halo exchange with interior rows).  Prepass rows are plane
+ * rows [row_begin, row_end) of [0, height); the replicated border rows are produced together with row 0 / row height-1.
+ * Filter rows must lie inside the plan's [row_begin, row_end) and need the prepass of rows [y - radius, y + radius). */
+int smc_denoiser_prepass_rows(smc_denoiser *d, int row_begin, int row_end);
+int smc_denoiser_filter_rows(smc_denoiser *d, int row_begin, int row_end);
+
+/* Host mirrors of the planes a plan was created with: {dev = HOST pointer of row 0, step = host pitch in bytes, 0 =
+ * tightly packed}.  Arrays have the same length and order as in smc_filter_desc; NULL arrays / NULL entries are skipped. */
+typedef struct smc_host_io {
+    const smc_plane *n, *mean, *m2, *m3, *film_ptrs; /* uploaded (Estimator::uploadBuffers, EST.cpp:163-178) */
+    smc_plane film;                                  /* uploaded */
+    const smc_plane *gbufs;                          /* uploaded */
+    const smc_plane *film_filtered_ptrs;             /* downloaded (Estimator::downloadBuffers) */
+    smc_plane film_filtered;                         /* downloaded */
+    const smc_plane *mean_corr, *disc;               /* optional downloads */
+} smc_host_io;
+/* Estimator::Upload -> Denoise -> Download (EST.cpp:409-489) as ONE pipelined call: host planes are uploaded in row
+ * chunks on a copy stream while earlier chunks are prepassed and filtered on the context stream and finished output rows
+ * are downloaded on a third stream, so PCIe transfers overlap the kernels.  Results are identical to upload-all, run,
+ * download-all.  Asynchronous: the context stream joins the copy streams, smc_synchronize() completes everything.
+ * Host memory should be pinned (smc_host_alloc / smc_host_register); pageable memory works but does not overlap.
+ * chunk_rows = 0 picks whole waves of the filter grid (about 8 chunks per frame). */
+int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int chunk_rows);
 /* Record rows for halo exchange, image z.  which: 0 = own top `radius` rows (send up), 1 = own bottom `radius`
  * rows (send down), 2 = halo above row 0 (receive from the rank above), 3 = halo below the last row (receive from
  * the rank below).  Each region is one contiguous block of *bytes on the device. */

@@ -47,6 +47,13 @@ class FilterDesc(C.Structure):
                 ("halo_top_external", C.c_int), ("halo_bottom_external", C.c_int), ("kernel", C.c_int)]
 
 
+class HostIO(C.Structure):
+    _fields_ = [("n", C.POINTER(Plane)), ("mean", C.POINTER(Plane)), ("m2", C.POINTER(Plane)),
+                ("m3", C.POINTER(Plane)), ("film_ptrs", C.POINTER(Plane)), ("film", Plane),
+                ("gbufs", C.POINTER(Plane)), ("film_filtered_ptrs", C.POINTER(Plane)), ("film_filtered", Plane),
+                ("mean_corr", C.POINTER(Plane)), ("disc", C.POINTER(Plane))]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "smc_last_error": (C.c_char_p, []),
@@ -88,6 +95,9 @@ SIGNATURES = {
     "smc_denoiser_prepass": (C.c_int, [C.c_void_p]),
     "smc_denoiser_filter": (C.c_int, [C.c_void_p]),
     "smc_denoiser_run": (C.c_int, [C.c_void_p]),
+    "smc_denoiser_prepass_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "smc_denoiser_filter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "smc_denoiser_run_host": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_int]),
     "smc_denoiser_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "smc_denoiser_pairs": (C.c_uint64, [C.c_void_p]),
     "smc_denoiser_record_bytes": (C.c_size_t, [C.c_void_p]),

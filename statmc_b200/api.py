@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _capi as capi
-from ._capi import FilterDesc, Moments, Plane, check, lib
+from ._capi import FilterDesc, HostIO, Moments, Plane, check, lib
 
 
 class Context:
@@ -222,6 +222,44 @@ class Denoiser:
 
     def run(self) -> None:
         check(lib.smc_denoiser_run(self.h))
+
+    def prepass_rows(self, row_begin: int, row_end: int) -> None:
+        check(lib.smc_denoiser_prepass_rows(self.h, row_begin, row_end))
+
+    def filter_rows(self, row_begin: int, row_end: int) -> None:
+        check(lib.smc_denoiser_filter_rows(self.h, row_begin, row_end))
+
+    def run_host(self, *, n=None, mean=None, m2=None, m3=None, film_ptrs=None, film=None, gbufs=None,
+                 film_filtered_ptrs=None, film_filtered=None, mean_corr=None, disc=None, chunk_rows: int = 0) -> None:
+        """Estimator::Upload -> Denoise -> Download (estimator.cpp:409-489) as one pipelined, asynchronous call.
+        Every argument mirrors the constructor's device planes with HOST memory: a list of (host_ptr, pitch) tuples,
+        numpy arrays or PinnedArray (a single one for film / film_filtered).  Call ctx.synchronize() afterwards."""
+        keep = []
+
+        def hp(x) -> Plane:
+            if x is None:
+                return Plane(None, 0)
+            if isinstance(x, tuple):
+                return Plane(x[0], x[1])
+            a = x.array if isinstance(x, PinnedArray) else x
+            assert a.flags["C_CONTIGUOUS"]
+            keep.append(a)
+            return Plane(a.ctypes.data, a.strides[0])
+
+        def arr(lst):
+            if lst is None:
+                return C.POINTER(Plane)()
+            a = _plane_array([hp(x) for x in lst])
+            keep.append(a)
+            return a
+
+        io = HostIO()
+        io.n, io.mean, io.m2, io.m3, io.film_ptrs = arr(n), arr(mean), arr(m2), arr(m3), arr(film_ptrs)
+        io.film, io.gbufs = hp(film), arr(gbufs)
+        io.film_filtered_ptrs, io.film_filtered = arr(film_filtered_ptrs), hp(film_filtered)
+        io.mean_corr, io.disc = arr(mean_corr), arr(disc)
+        check(lib.smc_denoiser_run_host(self.h, C.byref(io), chunk_rows))
+        self._host_keep = keep  # the copies are asynchronous: keep the host arrays alive until the next call
 
     def halo(self, z: int, which: int):
         p, n = C.c_void_p(), C.c_size_t()

@@ -34,6 +34,11 @@ struct smc_denoiser {
     bool use_stream = false;
     int py = 4;
     char kernel_name[64] = "generic";
+    // host-pipelined run (smc_denoiser_run_host): host copy of the descriptor tables, copy streams, event pool
+    std::vector<SmcPtrStepSz> h_tables;
+    std::vector<unsigned char> h_gch;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> events;
 };
 
 static int taps_in_window(int r) {
@@ -227,6 +232,9 @@ extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc
     d->t_out = d->d_tables + 7 * pc;
     d->t_acc = desc->accepted ? d->d_tables + 8 * pc : nullptr;
     d->t_gbufs = d->d_tables + (size_t)fam * pc;
+    d->h_tables = h;
+    d->h_gch.assign(desc->gbuf_channels ? desc->gbuf_channels : nullptr,
+                    desc->gbuf_channels ? desc->gbuf_channels + desc->n_gbufs : nullptr);
     d->film = SmcPtrStepSz{(unsigned char *)desc->film.dev, desc->film.step, d->W, d->H};
     d->film_filtered = SmcPtrStepSz{(unsigned char *)desc->film_filtered.dev, desc->film_filtered.step, d->W, d->H};
 
@@ -245,27 +253,35 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     cudaFree(d->d_sw);
     cudaFree(d->d_rowrange);
     cudaFree(d->d_rec);
+    for (cudaEvent_t e : d->events) cudaEventDestroy(e);
+    if (d->s_in) cudaStreamDestroy(d->s_in);
+    if (d->s_out) cudaStreamDestroy(d->s_out);
     delete d;
 }
 
-extern "C" int smc_denoiser_prepass(smc_denoiser *d) {
-    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+// prepass over image rows [y0, y1); the replicated rows above row 0 / below row H-1 go with the first / last rows
+static int prepass_rows(smc_denoiser *d, int y0, int y1) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
     SmcPrepassParams p;
     p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->ptr_count; p.radius = d->radius; p.mode = d->mode;
     p.denoise_film = d->denoise_film; p.padX = d->padX; p.rec_pitch = d->rec_pitch;
     p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec; p.skip_top = d->skip_top; p.skip_bottom = d->skip_bottom;
+    p.pr_begin = y0 == 0 ? 0 : y0 + d->radius;
+    p.pr_end = y1 == d->H ? d->H + 2 * d->radius : y1 + d->radius;
     p.n = d->t_n; p.mean = d->t_mean; p.m2 = d->t_m2; p.m3 = d->t_m3; p.film_ptrs = d->t_film; p.film = d->film;
     p.n_gbufs = d->n_gbufs; p.gbufs = d->t_gbufs; p.gbuf_channels = d->d_gch; p.gbuf_dr_factors = d->d_gf;
     p.mean_corr = d->t_mc; p.disc = d->t_disc; p.lut = d->ctx->d_lut;
     return smc_launch_prepass(d->ctx, p);
 }
 
-extern "C" int smc_denoiser_filter(smc_denoiser *d) {
-    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+// filter over output rows [y0, y1)
+static int filter_rows(smc_denoiser *d, int y0, int y1) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
+    if (y1 <= y0) return SMC_OK;
     SmcFilterParams p;
     fill_filter_params(d, p);
+    p.row_begin = y0;
+    p.row_end = y1;
     if (d->use_stream) {
         const char *nm = nullptr;
         const int rc = smc_launch_filter_stream(d->ctx, p, d->d_rowrange, d->py, &nm);
@@ -276,10 +292,163 @@ extern "C" int smc_denoiser_filter(smc_denoiser *d) {
     return smc_launch_filter_generic(d->ctx, p);
 }
 
+static int check_rows(const smc_denoiser *d, int y0, int y1, int lo, int hi) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    if (y0 < lo || y1 > hi || y0 > y1) SMC_FAIL(SMC_ERR_INVALID, "bad row range [%d, %d) (allowed [%d, %d))", y0, y1, lo, hi);
+    return SMC_OK;
+}
+
+extern "C" int smc_denoiser_prepass(smc_denoiser *d) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    return prepass_rows(d, 0, d->H);
+}
+
+extern "C" int smc_denoiser_prepass_rows(smc_denoiser *d, int row_begin, int row_end) {
+    int rc = check_rows(d, row_begin, row_end, 0, d ? d->H : 0);
+    if (rc) return rc;
+    if (row_begin == row_end) return SMC_OK;
+    return prepass_rows(d, row_begin, row_end);
+}
+
+extern "C" int smc_denoiser_filter(smc_denoiser *d) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    return filter_rows(d, d->row_begin, d->row_end);
+}
+
+extern "C" int smc_denoiser_filter_rows(smc_denoiser *d, int row_begin, int row_end) {
+    int rc = check_rows(d, row_begin, row_end, d ? d->row_begin : 0, d ? d->row_end : 0);
+    if (rc) return rc;
+    return filter_rows(d, row_begin, row_end);
+}
+
 extern "C" int smc_denoiser_run(smc_denoiser *d) {
     int rc = smc_denoiser_prepass(d);
     if (rc) return rc;
     return smc_denoiser_filter(d);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-pipelined run: Estimator::Upload -> Denoise -> Download (estimator.cpp:409-489) as ONE call in which the
+// PCIe copies overlap the kernels.  The image is cut into row chunks; chunk k is uploaded on a copy stream while
+// chunk k-1 is prepassed and the rows whose whole window is already packed (y <= chunk_end - radius) are filtered on
+// the context stream, and finished output rows are downloaded on a third stream.  Results are identical to
+// upload-all / run / download-all: the same kernels run over the same rows, only in row order.
+// ---------------------------------------------------------------------------------------------------------
+static cudaEvent_t get_event(smc_denoiser *d, size_t i) {
+    while (d->events.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        d->events.push_back(e);
+    }
+    return d->events[i];
+}
+
+static int auto_chunk_rows(const smc_denoiser *d) {
+    const int rows = d->row_end - d->row_begin;
+    int chunk;
+    if (d->use_stream) {
+        // whole waves of the persistent grid per chunk: tiles(chunk) = k * grid, about 8 chunks per frame
+        SmcFilterParams p;
+        fill_filter_params(d, p);
+        const int grid = smc_filter_stream_resident_ctas(p, d->py, d->ctx->sm_count);
+        const int tiles_x = (d->W + 255) / 256;
+        const long long total = (long long)tiles_x * ((rows + d->py - 1) / d->py);
+        long long k = (total / std::max(grid, 1) + 4) / 8;
+        if (k < 1) k = 1;
+        chunk = (int)(k * grid / tiles_x) * d->py;
+    } else {
+        chunk = ((rows / 8 + 7) / 8) * 8;
+    }
+    return std::max(chunk, std::max(2 * d->radius, 16));
+}
+
+extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int chunk_rows) {
+    if (!d || !io) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    if (d->tables_external) SMC_FAIL(SMC_ERR_UNSUPPORTED, "plan was built from device tables: host planes unknown");
+    if (d->skip_top || d->skip_bottom)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "record-halo exchange plans cannot be pipelined from the host in one call");
+    if (chunk_rows < 0) SMC_FAIL(SMC_ERR_INVALID, "chunk_rows < 0");
+    smc_context *ctx = d->ctx;
+    SMC_CUDA(cudaSetDevice(ctx->device));
+    if (!d->s_in) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+    if (!d->s_out) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+    const int pc = d->ptr_count, H = d->H, r = d->radius;
+    if (chunk_rows == 0) chunk_rows = auto_chunk_rows(d);
+
+    struct Xfer { const SmcPtrStepSz *dev; smc_plane host; size_t row_bytes; };
+    std::vector<Xfer> ups, downs;
+    auto add = [&](std::vector<Xfer> &v, const SmcPtrStepSz *dev, const smc_plane *host, size_t px_bytes) {
+        if (!host || !host->dev || !dev->data) return;
+        for (const Xfer &x : v)
+            if (x.dev->data == dev->data) return;  // aliased planes (mean == film-mean when !transform) move once
+        Xfer x{dev, *host, (size_t)d->W * px_bytes};
+        if (x.host.step == 0) x.host.step = x.row_bytes;
+        v.push_back(x);
+    };
+    const SmcPtrStepSz *T = d->h_tables.data();
+    const size_t cb = (size_t)d->C * 4;
+    for (int i = 0; i < pc; i++) {
+        add(ups, T + 0 * pc + i, io->n ? io->n + i : nullptr, 4);
+        add(ups, T + 1 * pc + i, io->mean ? io->mean + i : nullptr, cb);
+        add(ups, T + 2 * pc + i, io->m2 ? io->m2 + i : nullptr, cb);
+        add(ups, T + 3 * pc + i, io->m3 ? io->m3 + i : nullptr, cb);
+        add(ups, T + 4 * pc + i, io->film_ptrs ? io->film_ptrs + i : nullptr, cb);
+        add(downs, T + 5 * pc + i, io->mean_corr ? io->mean_corr + i : nullptr, cb);
+        add(downs, T + 6 * pc + i, io->disc ? io->disc + i : nullptr, cb);
+    }
+    add(ups, &d->film, &io->film, 12);
+    for (int g = 0; g < d->n_gbufs; g++)
+        add(ups, T + 9 * (size_t)pc + g, io->gbufs ? io->gbufs + g : nullptr, (size_t)d->h_gch[g] * 4);
+    const size_t n_aux_downs = downs.size();  // mean-corr / discriminator rows are final right after the prepass
+    for (int i = 0; i < pc; i++) add(downs, T + 7 * pc + i, io->film_filtered_ptrs ? io->film_filtered_ptrs + i : nullptr, cb);
+    add(downs, &d->film_filtered, &io->film_filtered, 12);
+
+    size_t ev = 0;
+    cudaEvent_t e_begin = get_event(d, ev++);
+    if (!e_begin) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
+    // the copy streams start after whatever is already queued on the context stream
+    SMC_CUDA(cudaEventRecord(e_begin, ctx->stream));
+    SMC_CUDA(cudaStreamWaitEvent(d->s_in, e_begin, 0));
+    SMC_CUDA(cudaStreamWaitEvent(d->s_out, e_begin, 0));
+
+    int filtered_to = d->row_begin;  // output rows < filtered_to are done
+    for (int a = 0; a < H; a += chunk_rows) {
+        const int b = std::min(H, a + chunk_rows);
+        for (const Xfer &x : ups)
+            SMC_CUDA(cudaMemcpy2DAsync(x.dev->data + (size_t)a * x.dev->step, x.dev->step,
+                                       (const char *)x.host.dev + (size_t)a * x.host.step, x.host.step, x.row_bytes,
+                                       b - a, cudaMemcpyHostToDevice, d->s_in));
+        cudaEvent_t e_up = get_event(d, ev++), e_f = get_event(d, ev++);
+        if (!e_up || !e_f) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
+        SMC_CUDA(cudaEventRecord(e_up, d->s_in));
+        SMC_CUDA(cudaStreamWaitEvent(ctx->stream, e_up, 0));
+        int rc = prepass_rows(d, a, b);
+        if (rc) return rc;
+        // output row y reads record rows y-r .. y+r-1: complete once rows < b are packed  <=>  y <= b - r
+        const int f_end = b == H ? d->row_end : std::min(d->row_end, std::max(filtered_to, b - r + 1));
+        const int f_begin = filtered_to;
+        if (f_end > f_begin) {
+            rc = filter_rows(d, f_begin, f_end);
+            if (rc) return rc;
+            filtered_to = f_end;
+        }
+        SMC_CUDA(cudaEventRecord(e_f, ctx->stream));
+        SMC_CUDA(cudaStreamWaitEvent(d->s_out, e_f, 0));
+        for (size_t i = 0; i < downs.size(); i++) {
+            const Xfer &x = downs[i];
+            const int y0 = i < n_aux_downs ? a : f_begin, y1 = i < n_aux_downs ? b : f_end;
+            if (y1 <= y0) continue;
+            SMC_CUDA(cudaMemcpy2DAsync((char *)x.host.dev + (size_t)y0 * x.host.step, x.host.step,
+                                       x.dev->data + (size_t)y0 * x.dev->step, x.dev->step, x.row_bytes, y1 - y0,
+                                       cudaMemcpyDeviceToHost, d->s_out));
+        }
+    }
+    // join: smc_synchronize(ctx) (or anything queued later on the context stream) covers the downloads
+    cudaEvent_t e_end = get_event(d, ev++);
+    if (!e_end) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
+    SMC_CUDA(cudaEventRecord(e_end, d->s_out));
+    SMC_CUDA(cudaStreamWaitEvent(ctx->stream, e_end, 0));
+    return SMC_OK;
 }
 
 extern "C" int smc_denoiser_halo(smc_denoiser *d, int z, int which, void **dev, size_t *bytes) {

@@ -25,6 +25,9 @@ namespace {
 constexpr int kTileW = 256;
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
+#ifndef SMC_STREAM_REFILL
+#define SMC_STREAM_REFILL 1  // 0: thread 0 refills a slot after waiting on its "empty" mbarrier; 1: the last warp to leave a slot refills it
+#endif
 #ifndef SMC_STREAM_MINB
 #define SMC_STREAM_MINB 2  // resident CTAs per SM the register allocation is bounded for
 #endif
@@ -70,6 +73,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// shared-memory counter: returns the old value; acq_rel at CTA scope orders this warp's reads of a ring slot before the
+// refill another warp (or this one) issues after seeing the count complete
+__device__ __forceinline__ uint32_t smem_inc_acq_rel(uint32_t *p) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
 }
 
 __device__ __forceinline__ SmcRec lds_rec(const unsigned char *p) {
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
     int2 *rowrange = (int2 *)(sw + g.sw_rows * p.sw_stride);
     uint64_t *full = (uint64_t *)(rowrange + g.sw_rows);
     uint64_t *empty = full + g.depth;
+    uint32_t *left = (uint32_t *)(empty + g.depth);  // warps that have left each slot (SMC_STREAM_REFILL == 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = p.radius;
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
         for (int s = 0; s < g.depth; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kWarps);
+            left[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -261,6 +274,17 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
                 }
             }
             __syncwarp();
+#if SMC_STREAM_REFILL == 1
+            // the last warp to leave the slot refills it at once: nobody ever blocks on a free slot, and a slow warp
+            // does not delay the loads of the others
+            if (lane == 0 && smem_inc_acq_rel(&left[s]) == kWarps - 1) {
+                left[s] = 0;  // ordered before the next round of increments by the full-barrier completion
+                if (pos + g.depth < total_pos) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(pos + g.depth);
+                }
+            }
+#else
             if (lane == 0) mbar_arrive(&empty[s]);
             // refill with a lag of one row: the slot of position pos-1 is free once every warp has left it
             if (producer && pos >= 1 && pos - 1 + g.depth < total_pos) {
@@ -268,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
                 mbar_wait(&empty[(int)(q % g.depth)], (uint32_t)((q / g.depth) & 1));
                 issue(q + g.depth);
             }
+#endif
         }
 
         // write the tile (stat_denoiser.cu:341-344); centre fix-up: the reference gives the centre tap weight 1
@@ -302,10 +327,14 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
 }
 
 template <typename K>
-int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &g, size_t smem) {
+int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &g, size_t smem, int *query_per_sm) {
     SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem));
+    if (query_per_sm) {
+        *query_per_sm = per_sm;
+        return SMC_OK;
+    }
     if (per_sm < 1) SMC_FAIL(SMC_ERR_CUDA, "streaming filter does not fit on an SM (smem %zu)", smem);
     // persistent grid: one wave of resident CTAs, each walking tiles b, b + grid, ... (neighbouring tiles run
     // concurrently, so the rows they share are fetched from HBM once and served from L2)
@@ -316,9 +345,9 @@ int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &
 }
 
 template <int NG, int PY, int MODE>
-int launch(smc_context *ctx, const SmcFilterParams &p, const StreamGeom &g, size_t smem) {
-    if (p.accepted != nullptr) return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, true>, p, g, smem);
-    return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, false>, p, g, smem);
+int launch(smc_context *ctx, const SmcFilterParams &p, const StreamGeom &g, size_t smem, int *q) {
+    if (p.accepted != nullptr) return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, true>, p, g, smem, q);
+    return launch_k(ctx, filter_stream_kernel<NG, PY, MODE, false>, p, g, smem, q);
 }
 
 }  // namespace
@@ -336,7 +365,7 @@ static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, siz
     g.seg_max_rec = kTileW + 2 * p.radius + 4;
     g.slot_bytes = (((g.seg_max_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
     g.sw_rows = 2 * p.radius + 2 * p.sw_margin_y;
-    const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 2 * 8 * 8 + 64;
+    const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 2 * 8 * 8 + 8 * 4 + 64;
     // Ring depth / residency (measured on B200, 4K r=20, profiles/r1_variants.md): 3 CTAs per SM with a 3-deep ring
     // beat 2 CTAs with 4 slots when PY = 2 (166 registers per thread allow 3 CTAs); PY = 4 (250 registers) is limited to
     // 2 CTAs by the register file, where 4 slots fit.  Each CTA also reserves 1 KB of shared memory.
@@ -375,8 +404,23 @@ bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const c
     return true;
 }
 
+static int stream_dispatch(smc_context *ctx, const SmcFilterParams &p, const int2 *d_rowrange, int py,
+                           const char **name, int *query_per_sm);
+
 int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *d_rowrange, int py,
                              const char **name) {
+    return stream_dispatch(ctx, p, d_rowrange, py, name, nullptr);
+}
+
+int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count) {
+    int per_sm = 0;
+    if (stream_dispatch(nullptr, p, nullptr, py, nullptr, &per_sm) != SMC_OK || per_sm < 1) per_sm = 1;
+    return per_sm * sm_count;
+}
+
+static int stream_dispatch(smc_context *ctx, const SmcFilterParams &p, const int2 *d_rowrange, int py,
+                           const char **name, int *query_per_sm) {
+    int *q = query_per_sm;
     StreamGeom g;
     size_t smem = 0;
     if (!stream_geometry(p, py, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: geometry not supported");
@@ -387,9 +431,9 @@ int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const i
 #define SMC_STREAM_CASE(NGv)                                                                                          \
     case NGv:                                                                                                         \
         if (py == 4) {                                                                                                \
-            return p.mode == 0 ? launch<NGv, 4, 0>(ctx, p, g, smem) : launch<NGv, 4, 1>(ctx, p, g, smem); \
+            return p.mode == 0 ? launch<NGv, 4, 0>(ctx, p, g, smem, q) : launch<NGv, 4, 1>(ctx, p, g, smem, q); \
         } else {                                                                                                      \
-            return p.mode == 0 ? launch<NGv, 2, 0>(ctx, p, g, smem) : launch<NGv, 2, 1>(ctx, p, g, smem); \
+            return p.mode == 0 ? launch<NGv, 2, 0>(ctx, p, g, smem, q) : launch<NGv, 2, 1>(ctx, p, g, smem, q); \
         }
     switch (p.NG) {
         SMC_STREAM_CASE(0)

@@ -122,6 +122,7 @@ struct SmcPrepassParams {
     size_t rec_image_stride;
     unsigned char *rec;
     int skip_top, skip_bottom;  // halo rows filled externally
+    int pr_begin, pr_end;       // padded record rows [pr_begin, pr_end) to produce (padded row pr holds y = pr - radius)
     const SmcPtrStepSz *n, *mean, *m2, *m3, *film_ptrs;
     SmcPtrStepSz film;
     int n_gbufs;
@@ -138,6 +139,8 @@ int smc_launch_filter_generic(smc_context *ctx, const SmcFilterParams &p);
 // rowrange: device array, one {jlo, jhi} per spatial-table row; py: output rows per thread (2 or 4)
 int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *rowrange, int py,
                              const char **name);
+// CTAs of the persistent streaming grid that are resident at once (occupancy x SM count)
+int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count);
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name);
 #define SMC_SW_MARGIN_Y 3
 #define SMC_SW_MARGIN_X 2

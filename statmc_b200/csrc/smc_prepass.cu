@@ -35,7 +35,7 @@ template <int C>
 __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     const int col_blocks = (p.rec_pitch + blockDim.x - 1) / blockDim.x;
     const int pc = (blockIdx.x % col_blocks) * blockDim.x + threadIdx.x;  // padded column
-    const int pr = blockIdx.x / col_blocks;                                // padded row: y = pr - radius
+    const int pr = p.pr_begin + blockIdx.x / col_blocks;                   // padded row: y = pr - radius
     const int z = blockIdx.y;
     if (pc >= p.rec_pitch) return;
     const int yy = pr - p.radius;
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
 }  // namespace
 
 int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p) {
-    const dim3 block(256), grid(((p.rec_pitch + 255) / 256) * (p.H + 2 * p.radius), p.ptr_count);
+    if (p.pr_end <= p.pr_begin) return SMC_OK;
+    const dim3 block(256), grid(((p.rec_pitch + 255) / 256) * (p.pr_end - p.pr_begin), p.ptr_count);
     if (p.C == 3) prepass_kernel<3><<<grid, block, 0, ctx->stream>>>(p);
     else prepass_kernel<1><<<grid, block, 0, ctx->stream>>>(p);
     SMC_CHECK_LAUNCH(ctx);

@@ -229,3 +229,33 @@ def test_record_halo_exchange_mode(ctx):
     ctx.synchronize()
     got = np.concatenate([halves[0][1].download(), halves[1][1].download()], axis=0)
     assert bits_equal(got, full)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("chunk", [0, 1, 7, 24, 1000])
+def test_host_pipelined_run_is_exact(ctx, kernel, chunk):
+    # smc_denoiser_run_host (chunked upload / prepass / filter / download on three streams) == upload-all, run, download-all
+    from statmc_b200.api import PinnedArray
+    W, H, r, sd = 300, 70, 9, 4.0
+    b = synth.moment_buffers(W, H, n=32, config_id=61)
+    ref = denoise_host(ctx, b, radius=r, sd=sd, kernel=kernel, want_aux=True)
+    names = ("n", "mean", "m2", "m3", "film", "normal", "albedo")
+    pin = {k: PinnedArray(b[k].shape, b[k].dtype) for k in names}
+    for k in names:
+        pin[k].array[...] = b[k]
+    dev = {k: Buffer(ctx, H, W, 1 if b[k].ndim == 2 else 3, b[k].dtype, k) for k in names}  # zero-filled: no stale data
+    out, mc, dc = Buffer(ctx, H, W, 3), Buffer(ctx, H, W, 3), Buffer(ctx, H, W, 3)
+    h_out, h_mc, h_dc = (PinnedArray((H, W, 3), np.float32) for _ in range(3))
+    dn = Denoiser(ctx, channels=3, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2, n=[dev["n"]],
+                  mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]], film=dev["film"],
+                  gbufs=[dev["normal"], dev["albedo"]], gbuf_dr_factors=[-0.5 / 0.01, -0.5 / 0.0004],
+                  film_filtered_ptrs=[out], film_filtered=out, denoise_film=True, kernel=kernel, mean_corr=[mc], disc=[dc])
+    for rep in range(2):  # twice: the second call must order itself after the first one's kernels and copies
+        h_out.array[...] = -1.0
+        dn.run_host(n=[pin["n"]], mean=[pin["mean"]], m2=[pin["m2"]], m3=[pin["m3"]], film_ptrs=[pin["film"]],
+                    film=pin["film"], gbufs=[pin["normal"], pin["albedo"]], film_filtered=h_out, mean_corr=[h_mc],
+                    disc=[h_dc], chunk_rows=chunk)
+        ctx.synchronize()
+        assert bits_equal(h_out.array, ref["film_f"]), (kernel, chunk, rep)
+        assert bits_equal(h_mc.array, ref["mean_corr"]) and bits_equal(h_dc.array, ref["disc"])
+    dn.close()
