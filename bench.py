@@ -361,6 +361,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(W, radius, sd, n)
         print(json.dumps(res), flush=True)
+    dn.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

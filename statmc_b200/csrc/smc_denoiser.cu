@@ -39,6 +39,8 @@ struct smc_denoiser {
     std::vector<unsigned char> h_gch;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
+    int *d_tile_counter = nullptr;
+    unsigned long long *d_trace = nullptr;  // SMC_STREAM_TRACE=<file>: per-CTA timeline of the last streaming launch
 };
 
 static int taps_in_window(int r) {
@@ -102,7 +104,7 @@ static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p) {
     p.row_begin = d->row_begin; p.row_end = d->row_end;
     p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec;
     p.sw = d->d_sw; p.sw_stride = d->sw_stride; p.sw_margin_y = SMC_SW_MARGIN_Y; p.sw_margin_x = SMC_SW_MARGIN_X;
-    p.out_ptrs = d->t_out; p.film_filtered = d->film_filtered; p.accepted = d->t_acc;
+    p.out_ptrs = d->t_out; p.film_filtered = d->film_filtered; p.accepted = d->t_acc; p.trace = d->d_trace; p.tile_counter = d->d_tile_counter;
 }
 
 static int select_kernel(smc_denoiser *d) {
@@ -119,6 +121,11 @@ static int select_kernel(smc_denoiser *d) {
     // radius tried (profiles/r1_variants.md).  SMC_STREAM_PY=4 selects the 2 x 4 variant for experiments.
     d->py = 2;
     if (const char *e = getenv("SMC_STREAM_PY")) d->py = atoi(e) == 4 ? 4 : 2;
+    if (!d->d_tile_counter) SMC_CUDA(cudaMalloc(&d->d_tile_counter, sizeof(int)));
+    if (getenv("SMC_STREAM_TRACE") && !d->d_trace) {
+        SMC_CUDA(cudaMalloc(&d->d_trace, 4096 * 4 * sizeof(unsigned long long)));
+        SMC_CUDA(cudaMemset(d->d_trace, 0, 4096 * 4 * sizeof(unsigned long long)));
+    }
     snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", d->use_stream ? "stream" : "generic");
     return SMC_OK;
 }
@@ -247,12 +254,25 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
+    if (d->d_trace) {
+        if (const char *path = getenv("SMC_STREAM_TRACE")) {
+            std::vector<unsigned long long> h(4096 * 4);
+            if (cudaMemcpy(h.data(), d->d_trace, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+                if (FILE *f = fopen(path, "w")) {
+                    for (int i = 0; i < 4096 && h[4 * i]; i++)
+                        fprintf(f, "%d %llu %llu %llu %llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                    fclose(f);
+                }
+        }
+        cudaFree(d->d_trace);
+    }
     if (!d->tables_external) cudaFree(d->d_tables);
     cudaFree(d->d_gch);
     cudaFree(d->d_gf);
     cudaFree(d->d_sw);
     cudaFree(d->d_rowrange);
     cudaFree(d->d_rec);
+    cudaFree(d->d_tile_counter);
     for (cudaEvent_t e : d->events) cudaEventDestroy(e);
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);

@@ -25,9 +25,6 @@ namespace {
 constexpr int kTileW = 256;
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-#ifndef SMC_STREAM_REFILL
-#define SMC_STREAM_REFILL 1  // 0: thread 0 refills a slot after waiting on its "empty" mbarrier; 1: the last warp to leave a slot refills it
-#endif
 #ifndef SMC_STREAM_MINB
 #define SMC_STREAM_MINB 2  // resident CTAs per SM the register allocation is bounded for
 #endif
@@ -156,8 +153,8 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
     float *sw = (float *)(ring + (size_t)g.depth * g.slot_bytes);
     int2 *rowrange = (int2 *)(sw + g.sw_rows * p.sw_stride);
     uint64_t *full = (uint64_t *)(rowrange + g.sw_rows);
-    uint64_t *empty = full + g.depth;
-    uint32_t *left = (uint32_t *)(empty + g.depth);  // warps that have left each slot (SMC_STREAM_REFILL == 1)
+    uint32_t *left = (uint32_t *)(full + 8);              // warps that have left each slot
+    volatile int *tile_ids = (volatile int *)(left + 8);  // [4]: tiles of this CTA's sequence, indexed by (sequence number & 3)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = p.radius;
@@ -165,25 +162,37 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
 
     for (int i = threadIdx.x; i < g.sw_rows * p.sw_stride; i += kThreads) sw[i] = p.sw[i];
     for (int i = threadIdx.x; i < g.sw_rows; i += kThreads) rowrange[i] = g.rowrange[i];
+    // Dynamic tile scheduling: the first tile is the CTA's index, every further one comes from a global counter, fetched
+    // two tiles ahead so that the row stream never stalls at a tile boundary.  (With a static round-robin assignment the
+    // CTAs sharing an SM finish far apart -- the warp scheduler favours one of them -- and the SM idles through a long
+    // tail: measured 7.2 / 8.9 / 11.4 ms for the three CTAs of an SM at 4K.)
+    auto next_tile = [&]() { return (int)gridDim.x + atomicAdd(p.tile_counter, 1); };
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.depth; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWarps);
             left[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tile_ids[0] = (int)blockIdx.x;
+        tile_ids[1] = next_tile();
     }
     __syncthreads();
+    if (tile_ids[0] >= g.total_tiles) return;
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[4 * blockIdx.x + 0] = t;
+        p.trace[4 * blockIdx.x + 2] = smid;
+    }
 
-    const int my_tiles = (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    if (my_tiles <= 0) return;
-    const long long total_pos = (long long)my_tiles * g.nr;  // positions of this CTA's row stream
-    const bool producer = (threadIdx.x == 0);
-
-    // issue the copy for stream position `q`
+    // issue the copy for stream position `q` (row q % nr of the CTA's tile number q / nr); nothing past the last tile
     auto issue = [&](long long q) {
         const int tl = (int)(q / g.nr), i = (int)(q - (long long)tl * g.nr);
-        const TileCoord tc = tile_coord((int)blockIdx.x + tl * (int)gridDim.x, g, p.row_begin, PY);
+        const int t = tile_ids[tl & 3];
+        if (t >= g.total_tiles) return;
+        const TileCoord tc = tile_coord(t, g, p.row_begin, PY);
         const unsigned char *src;
         uint32_t bytes;
         seg_of(p, tc, i, src, bytes, g.seg_max_rec);
@@ -191,12 +200,18 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
         mbar_expect_tx(&full[s], bytes);
         bulk_g2s(ring + (size_t)s * g.slot_bytes, src, bytes, &full[s]);
     };
-    if (producer)
-        for (long long q = 0; q < min((long long)g.depth, total_pos); q++) issue(q);
+    if (threadIdx.x == 0)
+        for (long long q = 0; q < g.depth; q++) issue(q);
 
     long long pos = 0;
-    for (int tl = 0; tl < my_tiles; tl++) {
-        const TileCoord tc = tile_coord((int)blockIdx.x + tl * (int)gridDim.x, g, p.row_begin, PY);
+    int tl = 0;
+    for (;; tl++) {
+        const int tile = tile_ids[tl & 3];
+        if (tile >= g.total_tiles) break;
+        // tile tl+1 is already known (the copies of its first rows are issued during this tile); fetch tile tl+2.  Its
+        // slot last held tile tl-2, which every warp has left: warps drift by fewer than `depth` <= nr rows.
+        if (threadIdx.x == 0) tile_ids[(tl + 2) & 3] = next_tile();
+        const TileCoord tc = tile_coord(tile, g, p.row_begin, PY);
         const unsigned char *img = p.rec + (size_t)tc.z * p.rec_image_stride;
         const int xf = tc.x0 + warp * 64 + 2 * lane;  // first of this thread's two columns
         const bool warp_active = tc.x0 + warp * 64 < p.W;
@@ -274,25 +289,13 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
                 }
             }
             __syncwarp();
-#if SMC_STREAM_REFILL == 1
             // the last warp to leave the slot refills it at once: nobody ever blocks on a free slot, and a slow warp
             // does not delay the loads of the others
             if (lane == 0 && smem_inc_acq_rel(&left[s]) == kWarps - 1) {
                 left[s] = 0;  // ordered before the next round of increments by the full-barrier completion
-                if (pos + g.depth < total_pos) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(pos + g.depth);
-                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(pos + g.depth);
             }
-#else
-            if (lane == 0) mbar_arrive(&empty[s]);
-            // refill with a lag of one row: the slot of position pos-1 is free once every warp has left it
-            if (producer && pos >= 1 && pos - 1 + g.depth < total_pos) {
-                const long long q = pos - 1;
-                mbar_wait(&empty[(int)(q % g.depth)], (uint32_t)((q / g.depth) & 1));
-                issue(q + g.depth);
-            }
-#endif
         }
 
         // write the tile (stat_denoiser.cu:341-344); centre fix-up: the reference gives the centre tap weight 1
@@ -324,6 +327,15 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
             }
         }
     }
+    if (p.trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[4 * blockIdx.x + 1] = t;
+            p.trace[4 * blockIdx.x + 3] = tl;
+        }
+    }
 }
 
 template <typename K>
@@ -339,6 +351,7 @@ int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &
     // persistent grid: one wave of resident CTAs, each walking tiles b, b + grid, ... (neighbouring tiles run
     // concurrently, so the rows they share are fetched from HBM once and served from L2)
     const int grid = (int)std::min<long long>(g.total_tiles, (long long)per_sm * ctx->sm_count);
+    SMC_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), ctx->stream));
     k<<<grid, kThreads, smem, ctx->stream>>>(p, g);
     SMC_CHECK_LAUNCH(ctx);
     return SMC_OK;
@@ -365,7 +378,7 @@ static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, siz
     g.seg_max_rec = kTileW + 2 * p.radius + 4;
     g.slot_bytes = (((g.seg_max_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
     g.sw_rows = 2 * p.radius + 2 * p.sw_margin_y;
-    const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 2 * 8 * 8 + 8 * 4 + 64;
+    const size_t fixed = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8 + 8 * 8 + 8 * 4 + 4 * 4 + 64;
     // Ring depth / residency (measured on B200, 4K r=20, profiles/r1_variants.md): 3 CTAs per SM with a 3-deep ring
     // beat 2 CTAs with 4 slots when PY = 2 (166 registers per thread allow 3 CTAs); PY = 4 (250 registers) is limited to
     // 2 CTAs by the register file, where 4 slots fit.  Each CTA also reserves 1 KB of shared memory.
@@ -386,6 +399,10 @@ static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, siz
     if (want >= 2 && want <= 8) {
         g.depth = want;
         smem = (size_t)want * g.slot_bytes + fixed;
+    }
+    if (g.depth > g.nr) {  // warps drift by fewer than `depth` rows; the tile-id ring relies on that being at most one tile
+        g.depth = g.nr;
+        smem = (size_t)g.depth * g.slot_bytes + fixed;
     }
     return smem <= 220 * 1024;
 }

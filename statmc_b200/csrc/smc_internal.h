@@ -114,6 +114,8 @@ struct SmcFilterParams {
     const SmcPtrStepSz *out_ptrs;  // film_filtered_ptrs table (device)
     SmcPtrStepSz film_filtered;    // "film-f"
     const SmcPtrStepSz *accepted;  // optional, may be null
+    int *tile_counter;             // streaming kernel: global tile counter (dynamic scheduling), reset before each launch
+    unsigned long long *trace;     // debug (SMC_STREAM_TRACE): per CTA {start ns, end ns, smid, tiles}; normally null
 };
 
 struct SmcPrepassParams {

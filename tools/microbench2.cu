@@ -21,14 +21,17 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-struct Cen { float2 t01, d01, g0, g1, g2; float tz, dz; };
+struct Cen { float2 t01, d01, g0, g1, g2; float tz, dz, nc; };
 struct Rec { float2 m01, d01, g0, g1, g2, v01; float mz, dz, vz; };
 struct Acc { float n0, n1, n2, den; };
 
 template <int MODE>
 __device__ __forceinline__ void pair(const Cen &c, const Rec &r, float sw, Acc &a) {
     bool ok = true;
-    if (MODE != 2) {   // membership
+    if (MODE == 5 || MODE == 6 || MODE == 7) {  // FMA-form membership: fma(-tC, mI, dI) <= -dC
+        ok = (fmaf(c.t01.x, r.m01.x, r.d01.x) <= c.d01.x) & (fmaf(c.t01.y, r.m01.y, r.d01.y) <= c.d01.y) &
+             (fmaf(c.tz, r.mz, r.dz) <= c.dz);
+    } else if (MODE != 2) {   // membership
         if (MODE == 3) {  // scalar only
             ok = (c.d01.x + r.d01.x <= c.t01.x * r.m01.x) & (c.d01.y + r.d01.y <= c.t01.y * r.m01.y) & (c.dz + r.dz <= c.tz * r.mz);
         } else {
@@ -42,6 +45,12 @@ __device__ __forceinline__ void pair(const Cen &c, const Rec &r, float sw, Acc &
         float l = e0 * e0, h = e1 * e1;
         l = fmaf(e2, e2, l); h = fmaf(e3, e3, h); l = fmaf(e4, e4, l); h = fmaf(e5, e5, h);
         acc = l + h;
+    } else if (MODE == 4 || MODE == 6 || MODE == 7) {
+        // dot form: |gI|^2 (record) - 2 gI.gC + |gC|^2: acc = sum gI * (-2 gC) [+ nI + nC folded into sw]
+        float2 q = mul2(r.g0, c.g0);
+        q = fma2(r.g1, c.g1, q);
+        q = fma2(r.g2, c.g2, q);
+        acc = __fadd_rn(__fadd_rn(q.x, q.y), r.vz * 0.f + r.dz);  // + nI (a record slot)
     } else {
         float2 e = add2(r.g0, c.g0);
         float2 q = mul2(e, e);
@@ -51,7 +60,12 @@ __device__ __forceinline__ void pair(const Cen &c, const Rec &r, float sw, Acc &
     }
     float arg = __fsub_rn(sw, acc);
     float w = (MODE == 1) ? arg * 0.5f : ex2(arg);  // MODE 1: no MUFU
-    if (ok) {
+    if (MODE == 7) {
+        const float wm = ok ? w : 0.f;
+        float2 n01 = fma2(make_float2(wm, wm), r.v01, make_float2(a.n0, a.n1));
+        float2 n2d = fma2(make_float2(wm, wm), make_float2(r.vz, 1.f), make_float2(a.n2, a.den));
+        a.n0 = n01.x; a.n1 = n01.y; a.n2 = n2d.x; a.den = n2d.y;
+    } else if (ok) {
         a.n0 = fmaf(w, r.v01.x, a.n0); a.n1 = fmaf(w, r.v01.y, a.n1); a.n2 = fmaf(w, r.vz, a.n2); a.den += w;
     }
 }
@@ -62,7 +76,7 @@ __global__ void __launch_bounds__(128) k(float *out, const float *in, int iters,
     const float s = in[threadIdx.x & 31];
     for (int i = 0; i < NC; i++) {
         c[i].t01 = make_float2(s + i, s * 2 + i); c[i].d01 = make_float2(-s, -s - i); c[i].tz = s + 3; c[i].dz = -s * 3;
-        c[i].g0 = make_float2(s, -s); c[i].g1 = make_float2(s * .5f, s * .25f); c[i].g2 = make_float2(-s * .5f, s * .125f);
+        c[i].g0 = make_float2(s + 0.01f * i, -s); c[i].g1 = make_float2(s * .5f, s * .25f - 0.02f * i); c[i].g2 = make_float2(-s * .5f + 0.03f * i, s * .125f); c[i].nc = s * i;
         a[i] = {0, 0, 0, 0};
     }
     // records live in shared memory and are re-read every iteration at a varying index (4 x LDS.128 per record, as
@@ -75,7 +89,7 @@ __global__ void __launch_bounds__(128) k(float *out, const float *in, int iters,
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
-        const float4 *q = recs + (((it * 5 + threadIdx.x) & 255) << 2);
+        const float4 *q = recs + (((it * 5 + (threadIdx.x >> 5)) & 255) << 2);  // warp-uniform address: broadcast, no bank conflicts
         const float4 c0 = q[0], c1 = q[1], c2 = q[2], c3 = q[3];
         Rec r;
         r.m01 = make_float2(c0.x, c0.y); r.d01 = make_float2(c0.z, c0.w); r.mz = c1.x; r.dz = c1.y; r.vz = c1.z;
@@ -113,13 +127,17 @@ void run(const char *name, int ctas_per_sm) {
 }
 
 int main() {
-    for (int w = 1; w <= 4; w *= 2) {
+    for (int w = 1; w <= 4; w++) {
         run<0, 8>("full mix (packed)", w);
         run<1, 8>("no MUFU", w);
         run<2, 8>("no membership (no FSETP)", w);
         run<3, 8>("scalar only (no f32x2)", w);
+        run<4, 8>("dot-form weight", w);
+        run<5, 8>("fma membership", w);
+        run<6, 8>("dot-form + fma membership", w);
+        run<7, 8>("dot + fma memb + packed accum", w);
         run<0, 4>("full mix (packed)", w);
-        run<0, 2>("full mix (packed)", w);
+        run<6, 4>("dot-form + fma membership", w);
     }
     return 0;
 }
