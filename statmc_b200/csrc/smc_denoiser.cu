@@ -37,6 +37,7 @@ struct smc_denoiser {
     // host-pipelined run (smc_denoiser_run_host): host copy of the descriptor tables, copy streams, event pool
     std::vector<SmcPtrStepSz> h_tables;
     std::vector<unsigned char> h_gch;
+    std::vector<float> h_gf;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
     int *d_tile_counter = nullptr;
@@ -240,8 +241,10 @@ extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc
     d->t_acc = desc->accepted ? d->d_tables + 8 * pc : nullptr;
     d->t_gbufs = d->d_tables + (size_t)fam * pc;
     d->h_tables = h;
-    d->h_gch.assign(desc->gbuf_channels ? desc->gbuf_channels : nullptr,
-                    desc->gbuf_channels ? desc->gbuf_channels + desc->n_gbufs : nullptr);
+    if (desc->n_gbufs > 0) {
+        d->h_gch.assign(desc->gbuf_channels, desc->gbuf_channels + desc->n_gbufs);
+        d->h_gf.assign(desc->gbuf_dr_factors, desc->gbuf_dr_factors + desc->n_gbufs);
+    }
     d->film = SmcPtrStepSz{(unsigned char *)desc->film.dev, desc->film.step, d->W, d->H};
     d->film_filtered = SmcPtrStepSz{(unsigned char *)desc->film_filtered.dev, desc->film_filtered.step, d->W, d->H};
 
@@ -289,7 +292,12 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1) {
     p.pr_begin = y0 == 0 ? 0 : y0 + d->radius;
     p.pr_end = y1 == d->H ? d->H + 2 * d->radius : y1 + d->radius;
     p.n = d->t_n; p.mean = d->t_mean; p.m2 = d->t_m2; p.m3 = d->t_m3; p.film_ptrs = d->t_film; p.film = d->film;
-    p.n_gbufs = d->n_gbufs; p.gbufs = d->t_gbufs; p.gbuf_channels = d->d_gch; p.gbuf_dr_factors = d->d_gf;
+    p.gbufs = d->t_gbufs; p.NG = d->NG;
+    for (int g = 0, k = 0; g < d->n_gbufs; g++)
+        for (int c = 0; c < d->h_gch[g]; c++, k++) {
+            p.g_buf[k] = (unsigned char)g; p.g_ch[k] = (unsigned char)c; p.g_nch[k] = d->h_gch[g];
+            p.g_scale[k] = sqrtf(-d->h_gf[g] * 1.4426950408889634f);
+        }
     p.mean_corr = d->t_mc; p.disc = d->t_disc; p.lut = d->ctx->d_lut;
     return smc_launch_prepass(d->ctx, p);
 }
@@ -563,6 +571,8 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
             SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc failed");
         }
         if (n_gbufs > 0) {
+            d->h_gch.assign(gch.begin(), gch.begin() + n_gbufs);
+            d->h_gf.assign(gf.begin(), gf.begin() + n_gbufs);
             cudaMemcpy(d->d_gch, gch.data(), n_gbufs, cudaMemcpyHostToDevice);
             cudaMemcpy(d->d_gf, gf.data(), sizeof(float) * n_gbufs, cudaMemcpyHostToDevice);
         }

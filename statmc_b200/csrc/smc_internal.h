@@ -127,10 +127,12 @@ struct SmcPrepassParams {
     int pr_begin, pr_end;       // padded record rows [pr_begin, pr_end) to produce (padded row pr holds y = pr - radius)
     const SmcPtrStepSz *n, *mean, *m2, *m3, *film_ptrs;
     SmcPtrStepSz film;
-    int n_gbufs;
-    const SmcPtrStepSz *gbufs;
-    const unsigned char *gbuf_channels;  // device
-    const float *gbuf_dr_factors;        // device
+    const SmcPtrStepSz *gbufs;           // G-buffer plane descriptors (device table)
+    // flattened G-buffer channels (by value): channel k of the record comes from plane g_buf[k], component g_ch[k] of
+    // g_nch[k], multiplied by g_scale[k] = sqrtf(-drFactor * log2(e))
+    int NG;
+    unsigned char g_buf[7], g_ch[7], g_nch[7];
+    float g_scale[7];
     const SmcPtrStepSz *mean_corr, *disc;  // optional tables (device) or null
     const float *lut;
 };

@@ -12,6 +12,7 @@
 // mean-corr and discriminator planes are bit-identical to the reference kernels' output.
 #include <cfloat>
 
+#include "smc_fastdiv.cuh"
 #include "smc_internal.h"
 
 namespace {
@@ -31,7 +32,11 @@ __device__ __forceinline__ float lut_t(const float *__restrict__ lut, int idx) {
     return __ldg(lut + (idx < SMC_T_LUT_ENTRIES ? idx : SMC_T_LUT_ENTRIES - 1));
 }
 
-template <int C>
+// One thread per padded record.  Every global load of the pixel is issued before any arithmetic (the G-buffer set is a
+// compile-time unrolled list passed by value), so a thread has ~20 independent loads in flight: the kernel is bound by
+// HBM bandwidth, not by load latency or the XU pipe (the twelve IEEE divisions of a pixel share three divisors, see
+// smc_fastdiv.cuh).
+template <int C, int NG>
 __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     const int col_blocks = (p.rec_pitch + blockDim.x - 1) / blockDim.x;
     const int pc = (blockIdx.x % col_blocks) * blockDim.x + threadIdx.x;  // padded column
@@ -43,33 +48,61 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     const int y = min(max(yy, 0), p.H - 1);
     const int x = min(max(pc - p.padX, 0), p.W - 1);
     const bool own = (yy == y) && (pc - p.padX == x);  // not a replicated copy: also writes the API-visible planes
+    const bool welch = p.mode == SMC_MEMBER_WELCH;
+    const bool film_value = p.denoise_film && z == 0;
 
+    // ---- loads -------------------------------------------------------------------------------------------------
     const int n = rowi(p.n[z], y)[x];
-    const float nF = __int2float_rn(n);
-    const float nm1 = __fsub_rn(nF, 1.f);
-    const float *meanp = rowf(p.mean[z], y) + x * C;
-    const float *m2p = rowf(p.m2[z], y) + x * C;
-
-    float rec[SMC_REC_FLOATS];
-#pragma unroll
-    for (int i = 0; i < SMC_REC_FLOATS; i++) rec[i] = 0.f;
-
-    float m[C], d[C];
-    if (p.mode == SMC_MEMBER_WELCH) {
-        const float *m3p = rowf(p.m3[z], y) + x * C;
-        const float t = lut_t(p.lut, 2 * n - 3);
-        const float tt = __fmul_rn(t, t);
-        const float nn1 = __fmul_rn(nF, nm1);
+    float mean[C], m2[C], m3[C], val[C], film[3], g[NG > 0 ? NG : 1];
+    {
+        const float *meanp = rowf(p.mean[z], y) + x * C;
+        const float *m2p = rowf(p.m2[z], y) + x * C;
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            const float m2 = m2p[c];
-            const float s2 = __fdiv_rn(m2, nm1);  // stat_denoiser.cu:179
+            mean[c] = meanp[c];
+            m2[c] = m2p[c];
+            m3[c] = 0.f;
+            val[c] = 0.f;
+        }
+        if (welch) {
+            const float *m3p = rowf(p.m3[z], y) + x * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) m3[c] = m3p[c];
+        }
+        if (!(C == 3 && film_value)) {
+            const float *vp = rowf(p.film_ptrs[z], y) + x * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) val[c] = vp[c];
+        }
+        film[0] = film[1] = film[2] = 0.f;
+        if (film_value) {
+            const float *fp = rowf(p.film, y) + x * 3;
+            film[0] = fp[0]; film[1] = fp[1]; film[2] = fp[2];
+        }
+#pragma unroll
+        for (int k = 0; k < NG; k++) g[k] = rowf(p.gbufs[p.g_buf[k]], y)[x * p.g_nch[k] + p.g_ch[k]];
+    }
+    // t-quantile: stat_denoiser.cu:200-202 (Welch, index 2n-3) / :128 (Moon, index n-2)
+    const float t = lut_t(p.lut, welch ? 2 * n - 3 : n - 2);
+
+    // ---- arithmetic ----------------------------------------------------------------------------------------------
+    const float nF = __int2float_rn(n);
+    const float nm1 = __fsub_rn(nF, 1.f);
+    const float nn1 = __fmul_rn(nF, nm1);
+    const SmcDivisor d_nn1 = smc_divisor(nn1);
+    float m[C], d[C];
+    if (welch) {
+        const SmcDivisor d_nm1 = smc_divisor(nm1), d_n = smc_divisor(nF);
+        const float tt = __fmul_rn(t, t);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float s2 = smc_div(m2[c], d_nm1);  // stat_denoiser.cu:179
             // johnson_mean_corr, stat_denoiser.cu:114-116: s2 > FLT_EPSILON ? (m3 / nF) / (6.f * s2 * nF) : 0.f
             float corr = 0.f;
-            if (s2 > FLT_EPSILON) corr = __fdiv_rn(__fdiv_rn(m3p[c], nF), __fmul_rn(__fmul_rn(6.f, s2), nF));
-            m[c] = __fadd_rn(meanp[c], corr);  // :181
+            if (s2 > FLT_EPSILON) corr = __fdiv_rn(smc_div(m3[c], d_n), __fmul_rn(__fmul_rn(6.f, s2), nF));
+            m[c] = __fadd_rn(mean[c], corr);  // :181
             // :205  mean*mean - t*t*m2 / (nF*(nF-1.f))
-            d[c] = __fsub_rn(__fmul_rn(m[c], m[c]), __fdiv_rn(__fmul_rn(tt, m2), nn1));
+            d[c] = __fsub_rn(__fmul_rn(m[c], m[c]), smc_div(__fmul_rn(tt, m2[c]), d_nn1));
         }
         if (own) {
             if (p.mean_corr && p.mean_corr[z].data) {
@@ -85,45 +118,34 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
         }
     } else {
         // Moon et al. CI test, stat_denoiser.cu:125-131: t index n-2, se = t * sqrtf(m2 / (nF * (nF - 1.f)))
-        const float t = lut_t(p.lut, n - 2);
-        const float nn1 = __fmul_rn(nF, nm1);
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            m[c] = meanp[c];
-            d[c] = __fmul_rn(t, __fsqrt_rn(__fdiv_rn(m2p[c], nn1)));
+            m[c] = mean[c];
+            d[c] = __fmul_rn(t, __fsqrt_rn(smc_div(m2[c], d_nn1)));
         }
     }
 
+    float rec[SMC_REC_FLOATS];
+#pragma unroll
+    for (int i = 0; i < SMC_REC_FLOATS; i++) rec[i] = 0.f;
     if (C == 3) {
         rec[0] = m[0]; rec[1] = m[1]; rec[4] = m[C - 1];
         rec[2] = d[0]; rec[3] = d[1]; rec[5] = d[C - 1];
-        const float *v = (p.denoise_film && z == 0) ? rowf(p.film, y) + x * 3 : rowf(p.film_ptrs[z], y) + x * 3;
-        rec[8] = v[0]; rec[9] = v[1]; rec[6] = v[2];
+        rec[8] = film_value ? film[0] : val[0];
+        rec[9] = film_value ? film[1] : val[1];
+        rec[6] = film_value ? film[2] : val[C - 1];
     } else {
         rec[0] = m[0];
         rec[2] = d[0];
-        rec[4] = rowf(p.film_ptrs[z], y)[x];
-        if (p.denoise_film && z == 0) {
-            const float *v = rowf(p.film, y) + x * 3;
-            rec[8] = v[0]; rec[9] = v[1]; rec[6] = v[2];
-        }
+        rec[4] = val[0];
+        rec[8] = film[0]; rec[9] = film[1]; rec[6] = film[2];
     }
-
     // G-buffers, flattened and pre-scaled so that  sum_k (g'_C - g'_I)^2 = -log2(e) * sum_g drFactor_g |g_C - g_I|^2
     // (dr2, stat_denoiser.cu:90-112); the filter then needs one subtraction and one FMA per channel and no factor.
-    const int slots[7] = {10, 11, 12, 13, 14, 15, 7};
-    int k = 0;
-    for (int g = 0; g < p.n_gbufs; g++) {
-        const int gc = p.gbuf_channels[g];
-        const float scale = sqrtf(-p.gbuf_dr_factors[g] * 1.4426950408889634f);
-        const float *gp = rowf(p.gbufs[g], y) + x * gc;
-        for (int c = 0; c < gc; c++, k++) {
-            const float v = __fmul_rn(gp[c], scale);
+    // g_scale[k] = sqrtf(-drFactor * log2(e)) is computed once on the host.
+    constexpr int slots[7] = {10, 11, 12, 13, 14, 15, 7};
 #pragma unroll
-            for (int s = 0; s < 7; s++)
-                if (k == s) rec[slots[s]] = v;
-        }
-    }
+    for (int k = 0; k < NG; k++) rec[slots[k]] = __fmul_rn(g[k], p.g_scale[k]);
 
     unsigned char *row = p.rec + (size_t)z * p.rec_image_stride + (size_t)pr * smc_rec_row_bytes(p.rec_pitch);
 #pragma unroll
@@ -133,11 +155,25 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
 
 }  // namespace
 
+template <int C>
+static void launch_prepass_ng(const SmcPrepassParams &p, dim3 grid, dim3 block, cudaStream_t s) {
+    switch (p.NG) {
+        case 0: prepass_kernel<C, 0><<<grid, block, 0, s>>>(p); break;
+        case 1: prepass_kernel<C, 1><<<grid, block, 0, s>>>(p); break;
+        case 2: prepass_kernel<C, 2><<<grid, block, 0, s>>>(p); break;
+        case 3: prepass_kernel<C, 3><<<grid, block, 0, s>>>(p); break;
+        case 4: prepass_kernel<C, 4><<<grid, block, 0, s>>>(p); break;
+        case 5: prepass_kernel<C, 5><<<grid, block, 0, s>>>(p); break;
+        case 6: prepass_kernel<C, 6><<<grid, block, 0, s>>>(p); break;
+        default: prepass_kernel<C, 7><<<grid, block, 0, s>>>(p); break;
+    }
+}
+
 int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p) {
     if (p.pr_end <= p.pr_begin) return SMC_OK;
     const dim3 block(256), grid(((p.rec_pitch + 255) / 256) * (p.pr_end - p.pr_begin), p.ptr_count);
-    if (p.C == 3) prepass_kernel<3><<<grid, block, 0, ctx->stream>>>(p);
-    else prepass_kernel<1><<<grid, block, 0, ctx->stream>>>(p);
+    if (p.C == 3) launch_prepass_ng<3>(p, grid, block, ctx->stream);
+    else launch_prepass_ng<1>(p, grid, block, ctx->stream);
     SMC_CHECK_LAUNCH(ctx);
     return SMC_OK;
 }

@@ -10,7 +10,7 @@ import pytest
 from oracle import pyoracle as po
 from statmc_b200 import synth
 from statmc_b200.api import Buffer, MomentState
-from util import bits_equal, moment_rel_err
+from util import bits_equal, bits_equal_nan, moment_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -123,3 +123,30 @@ def test_calculate_mean_vars(ctx):
     st.calculate_mean_vars(out)
     ctx.synchronize()
     assert bits_equal(out.download(), po.calculate_mean_vars(b["n"], b["film_m2"]))
+
+
+@pytest.mark.parametrize("W,H,C,S", [(68, 23, 3, 21), (64, 8, 3, 8), (100, 3, 3, 5), (96, 5, 1, 19), (36, 7, 1, 3),
+                                     (256, 9, 3, 40)])
+def test_streamed_sample_path_bit_exact(ctx, W, H, C, S):
+    # rows*W*C*4 is a multiple of 16 here, so smc_accumulate takes the TMA-streamed kernel (per-warp bulk-copy rings);
+    # sizes cover partial last warps, S below / above the ring depth, and sample values that leave the fast-division
+    # range (zeros, denormal-scale, huge, inf) so that both division paths are compared with the CPU's IEEE division
+    assert (W * H * C * 4) % 16 == 0
+    rng = np.random.default_rng(W * 1000 + S)
+    x = rng.gamma(0.7, 2.0, size=(S, H, W, C)).astype(np.float32)
+    x[rng.random(x.shape) < 0.05] = 0.0
+    x[rng.random(x.shape) < 0.01] = 1e-30
+    x[rng.random(x.shape) < 0.01] = 3e19
+    x[0, 0, :4] = np.float32(1e-38)
+    x[S // 2, H - 1, W - 3:] = np.float32(np.inf)
+    for transform in (True, False):
+        st = MomentState(ctx, W, H, C, transform=transform)
+        o = po.new_state(H, W, C)
+        for part in (x[:S // 2], x[S // 2:]):
+            st.add_samples(part)
+            po.accumulate(o, part, transform=transform, use_sqrt=True)
+        got = st.download()
+        sq = (lambda a: a[..., 0]) if C == 1 else (lambda a: a)
+        assert np.array_equal(got["n"], o["n"].astype(np.int32))
+        for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+            assert bits_equal_nan(got[k], sq(o[k])), (k, transform)

@@ -27,6 +27,16 @@ def bits_equal(a, b):
     return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+def bits_equal_nan(a, b):
+    """bit equality, except that any NaN matches any NaN (CPU and GPU produce different NaN payloads / signs)."""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    both_nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all(both_nan | (a.view(np.uint32) == b.view(np.uint32))))
+
+
 def small_buffers(W=96, H=64, n=32, seed=11, vary_n=False):
     from statmc_b200 import synth
     return synth.moment_buffers(W, H, n=n, config_id=seed, vary_n=vary_n)
