@@ -160,6 +160,11 @@ int smc_merge_moments(smc_context *ctx, const smc_moments *dst, const smc_moment
 int smc_calculate_mean_vars(smc_context *ctx, int width, int height, int channels, smc_plane n, smc_plane m2,
                             smc_plane out);
 
+/* The reference's own argument list (CIP.hpp:745-754): every *_ptrs argument is a DEVICE-resident array of ptr_count
+ * 24-byte {data, step, cols, rows} descriptors (cv::cuda::PtrStepSzb); `stream` is a cudaStream_t. */
+int smc_calculate_mean_vars_device_tables(smc_context *ctx, int channels, int ptr_count, int width, int height,
+                                          const void *n_ptrs, const void *m2_ptrs, void *mean_var_ptrs, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Stage 2: statistical denoiser.  Replaces cv::cuda::stat_denoiser::filter<T> (CIP.hpp:756-799; SD.cu:397-475:
  * johnson_mean_corrs_kernel -> mean_discriminators_kernel -> filter_kernel) and Estimator::Denoise (EST.cpp:427-489).

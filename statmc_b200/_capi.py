@@ -90,6 +90,8 @@ SIGNATURES = {
                                  C.c_int]),
     "smc_merge_moments": (C.c_int, [C.c_void_p, C.POINTER(Moments), C.POINTER(Moments)]),
     "smc_calculate_mean_vars": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, Plane, Plane, Plane]),
+    "smc_calculate_mean_vars_device_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "smc_denoiser_create": (C.c_int, [C.c_void_p, C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]),
     "smc_denoiser_destroy": (None, [C.c_void_p]),
     "smc_denoiser_prepass": (C.c_int, [C.c_void_p]),

@@ -71,6 +71,23 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_cpp_tests() -> str:
+    """g++ build of tests/cpp/test_estimator.cpp (the C++ host layer include/statmc_b200.hpp over the C ABI) into
+    build/test_estimator; run on the GPU box by tests/test_cpp_host_gpu.py."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_estimator.cpp")
+    out = os.path.join(ROOT, "build", "test_estimator")
+    deps = [src, os.path.join(ROOT, "include", "statmc_b200.hpp"), os.path.join(ROOT, "include", "statmc_b200.h"), LIB]
+    if _newer(out, deps):
+        return out
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+           "-L", os.path.join(ROOT, "statmc_b200"), "-lstatmc_b200", "-Wl,-rpath,$ORIGIN/../statmc_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for test_estimator.cpp:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build_variant(name: str, defines: list[str]) -> str:
     """Experiment builds: statmc_b200/libstatmc_b200_<name>.so compiled with extra -D flags (A/B timing only;
     select with the environment variable SMC_LIB_VARIANT=<name>)."""
