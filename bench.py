@@ -123,8 +123,10 @@ def main():
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--radius", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 streaming")
-    ap.add_argument("--halo", default="exchange", choices=["exchange", "redundant"],
-                    help="N>1: exchange record halos over NVLink (NCCL send/recv) or carry raw halo rows per band")
+    ap.add_argument("--halo", default="peer", choices=["peer", "exchange", "redundant"],
+                    help="N>1: peer = the prepass kernel stores edge records into the neighbours' halos over NVLink "
+                         "(peer-mapped memory, device flags; default); exchange = NCCL send/recv of record halos; "
+                         "redundant = carry raw halo rows per band, no device-to-device traffic")
     ap.add_argument("--gbufs", type=int, default=2, help="experiments: 0 = no G-buffers, 1 = normal only, 2 = normal + albedo")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-accum", action="store_true")
@@ -161,7 +163,8 @@ def main():
 
     # ---- this rank's band ------------------------------------------------------------------------------------
     y0, y1 = sharding.band_of(rank, world, H)
-    exchange = world > 1 and args.halo == "exchange"
+    exchange = world > 1 and args.halo in ("exchange", "peer")
+    peer = world > 1 and args.halo == "peer"
     if exchange:
         sharding.check_exchangeable(world, H, radius)
         lo, hi = y0, y1                                   # own rows only; record halos come from the neighbours
@@ -188,13 +191,16 @@ def main():
             dev[k].upload_ptr(pinned[k].ptr, 0, rows)
 
     halo_t = {}
-    if exchange:
+    if peer:
+        sharding.attach_peers(dist, rank, world, dn)
+    elif exchange:
         for which in range(4):
             p, nb = dn.halo(0, which)
             halo_t[which] = torch.as_tensor(RawCuda(p, nb), device=torch.device("cuda", local))
 
     def exchange_halos():
-        sharding.exchange_halos(dist, rank, world, halo_t[0], halo_t[1], halo_t[2], halo_t[3])
+        if not peer:  # peer mode: the prepass kernel has already stored our edge records into the neighbours' halos
+            sharding.exchange_halos(dist, rank, world, halo_t[0], halo_t[1], halo_t[2], halo_t[3])
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     filt_ms, pre_ms = [], []
@@ -250,24 +256,33 @@ def main():
     value = W * H / (ms_step * 1e-3) / 1e6
 
     # ---- end to end: host buffers through the C ABI -------------------------------------------------------------------
+    # Statistics start in (pinned) HOST memory, as in the reference (Estimator::Upload, estimator.cpp:409-416).  Each rank
+    # uploads its band plus `radius` raw halo rows (no device-to-device traffic: the prepass of the halo rows is recomputed,
+    # SURVEY 8e) through ONE pipelined call, smc_denoiser_run_host: row-chunked H2D / prepass + filter / D2H on three streams.
     e2e = None
     if not args.no_e2e:
-        # film-f host plane mirrors the device plane (all local rows); only the band's rows are written back
-        out_full = PinnedArray((rows, W, 3), np.float32) if not exchange else None
+        if exchange:
+            elo, ehi, _, _ = sharding.band_with_raw_halo(rank, world, H, radius)
+            erows = ehi - elo
+            eb = synth.moment_buffers(W, H, n=n, config_id=3, row0=elo, rows=erows, full_H=H)
+            epin = {k: PinnedArray(eb[k].shape, eb[k].dtype) for k in names}
+            for k in names:
+                epin[k].array[...] = eb[k]
+            edev = {k: Buffer(ctx, erows, W, 1 if eb[k].ndim == 2 else 3, eb[k].dtype, k) for k in names}
+            eout = Buffer(ctx, erows, W, 3, np.float32, "film-f")
+            edn = Denoiser(ctx, channels=3, width=W, height=erows, radius=radius, ds_factor=-0.5 / (sd * sd),
+                           n=[edev["n"]], mean=[edev["mean"]], m2=[edev["m2"]], m3=[edev["m3"]], film_ptrs=[edev["film"]],
+                           film=edev["film"], gbufs=[edev["normal"], edev["albedo"]][:args.gbufs],
+                           gbuf_dr_factors=[-0.5 / NORMAL_SD ** 2, -0.5 / ALBEDO_SD ** 2][:args.gbufs],
+                           film_filtered_ptrs=[eout], film_filtered=eout, denoise_film=True, row_begin=y0 - elo,
+                           row_end=y1 - elo, kernel=args.kernel)
+        else:
+            elo, erows, eb, epin, edn = lo, rows, bufs, pinned, dn
+        out_full = PinnedArray((erows, W, 3), np.float32)  # mirrors the device plane; only the band's rows are written back
 
         def e2e_step():
-            if exchange:
-                # record-halo exchange needs the neighbours' prepass: upload, prepass, swap, filter, download
-                upload_all()
-                dn.prepass()
-                exchange_halos()
-                dn.filter()
-                out.download_ptr(out_host.ptr, y0 - lo, y1 - y0)
-            else:
-                # Estimator::Upload -> Denoise -> Download as one pipelined C-ABI call (row chunks on three streams)
-                dn.run_host(n=[pinned["n"]], mean=[pinned["mean"]], m2=[pinned["m2"]], m3=[pinned["m3"]],
-                            film_ptrs=[pinned["film"]], film=pinned["film"],
-                            gbufs=[pinned["normal"], pinned["albedo"]][:args.gbufs], film_filtered=out_full)
+            edn.run_host(n=[epin["n"]], mean=[epin["mean"]], m2=[epin["m2"]], m3=[epin["m3"]], film_ptrs=[epin["film"]],
+                         film=epin["film"], gbufs=[epin["normal"], epin["albedo"]][:args.gbufs], film_filtered=out_full)
             ctx.synchronize()
         for _ in range(2):
             e2e_step()
@@ -282,7 +297,7 @@ def main():
         m2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(m2, op=dist.ReduceOp.MAX)
-        h2d = sum(int(bufs[k].nbytes) for k in names)
+        h2d = sum(int(eb[k].nbytes) for k in names)
         d2h = (y1 - y0) * W * 12
         tot = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -290,11 +305,14 @@ def main():
         e2e = {"value": W * H / (float(m2.item()) / k2 * 1e-3) / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
                "ms_per_step": float(m2.item()) / k2, "host_memory": "pinned",
-               "path": "upload, prepass, halo exchange, filter, download" if exchange else
-                       "smc_denoiser_run_host: row-chunked H2D / prepass+filter / D2H overlapped on three streams"}
+               "path": "smc_denoiser_run_host per rank: band + raw halo rows, row-chunked H2D / prepass+filter / D2H "
+                       "overlapped on three streams"}
         # sanity: the result that came back is the filtered film, not zeros
-        chk = out_host.array if exchange else out_full.array[y0 - lo:y1 - lo]
+        chk = out_full.array[y0 - elo:y1 - elo]
         assert np.isfinite(chk).all() and float(np.abs(chk).mean()) > 0
+        if exchange:
+            edn.close()
+            del edev, eout
 
     # ---- secondary metric: stat-accum Gsamples/s (stage 1) on this rank's band ----------------------------------------
     accum = None

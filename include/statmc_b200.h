@@ -240,6 +240,23 @@ int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int chunk_rows
  * rows (send down), 2 = halo above row 0 (receive from the rank above), 3 = halo below the last row (receive from
  * the rank below).  Each region is one contiguous block of *bytes on the device. */
 int smc_denoiser_halo(smc_denoiser *d, int z, int which, void **dev, size_t *bytes);
+/* Peer halos: the same exchange WITHOUT a separate copy step.  Each rank exports its record array once
+ * (smc_denoiser_peer_export; the 128-byte smc_peer_info travels to the neighbours by any means, e.g. an all-gather) and
+ * attaches the rank above (which = 0) and below (which = 1).  From then on smc_denoiser_prepass() stores the records of its
+ * top / bottom `radius` rows straight into the neighbours' halo rows over NVLink (peer-mapped memory, CUDA IPC) from inside
+ * the prepass kernel, and prepass / filter order themselves across GPUs with release/acquire flags in device memory:
+ * no NCCL call, no host synchronisation, nothing to do between prepass and filter.  The plan must have been created with
+ * halo_top_external / halo_bottom_external for the attached sides; every rank must call prepass and filter once per step.
+ * smc_denoiser_peer_attach_local is the same for two plans living in one process (same or peer-accessible devices). */
+typedef struct smc_peer_info {
+    unsigned char ipc_handle[64]; /* cudaIpcMemHandle_t of the record array */
+    uint64_t image_stride, flags_offset;
+    int32_t height, radius, rec_pitch, ptr_count, device;
+    int32_t reserved[7];
+} smc_peer_info;
+int smc_denoiser_peer_export(smc_denoiser *d, smc_peer_info *out);
+int smc_denoiser_peer_attach(smc_denoiser *d, int which, const smc_peer_info *info);
+int smc_denoiser_peer_attach_local(smc_denoiser *d, int which, smc_denoiser *other);
 /* Algorithmic work of one filter pass: pair evaluations = rows x width x taps(radius) x ptr_count. */
 uint64_t smc_denoiser_pairs(const smc_denoiser *d);
 size_t smc_denoiser_record_bytes(const smc_denoiser *d);

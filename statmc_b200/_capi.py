@@ -54,6 +54,12 @@ class HostIO(C.Structure):
                 ("mean_corr", C.POINTER(Plane)), ("disc", C.POINTER(Plane))]
 
 
+class PeerInfo(C.Structure):
+    _fields_ = [("ipc_handle", C.c_ubyte * 64), ("image_stride", C.c_uint64), ("flags_offset", C.c_uint64),
+                ("height", C.c_int32), ("radius", C.c_int32), ("rec_pitch", C.c_int32), ("ptr_count", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "smc_last_error": (C.c_char_p, []),
@@ -101,6 +107,9 @@ SIGNATURES = {
     "smc_denoiser_filter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "smc_denoiser_run_host": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_int]),
     "smc_denoiser_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "smc_denoiser_peer_export": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo)]),
+    "smc_denoiser_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PeerInfo)]),
+    "smc_denoiser_peer_attach_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "smc_denoiser_pairs": (C.c_uint64, [C.c_void_p]),
     "smc_denoiser_record_bytes": (C.c_size_t, [C.c_void_p]),
     "smc_denoiser_kernel_name": (C.c_char_p, [C.c_void_p]),

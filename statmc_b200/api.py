@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _capi as capi
-from ._capi import FilterDesc, HostIO, Moments, Plane, check, lib
+from ._capi import FilterDesc, HostIO, Moments, PeerInfo, Plane, check, lib
 
 
 class Context:
@@ -265,6 +265,20 @@ class Denoiser:
         p, n = C.c_void_p(), C.c_size_t()
         check(lib.smc_denoiser_halo(self.h, z, which, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def peer_export(self) -> bytes:
+        """128-byte description of this plan's record array for the neighbouring ranks (CUDA IPC handle inside)."""
+        info = PeerInfo()
+        check(lib.smc_denoiser_peer_export(self.h, C.byref(info)))
+        return bytes(info)
+
+    def peer_attach(self, which: int, info: bytes) -> None:
+        """which: 0 = the rank above, 1 = the rank below; `info` is that rank's peer_export()."""
+        pi = PeerInfo.from_buffer_copy(info)
+        check(lib.smc_denoiser_peer_attach(self.h, which, C.byref(pi)))
+
+    def peer_attach_local(self, which: int, other: "Denoiser") -> None:
+        check(lib.smc_denoiser_peer_attach_local(self.h, which, other.h))
 
     @property
     def pairs(self) -> int:

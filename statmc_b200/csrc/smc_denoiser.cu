@@ -41,6 +41,19 @@ struct smc_denoiser {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
     int *d_tile_counter = nullptr;
+    // peer halos (multi-GPU, one process per GPU or several plans in one process): flags live behind the records in the
+    // same allocation so that one IPC handle covers both.  flags: [0] ready_from_up [1] ready_from_down [2] free_from_up
+    // [3] free_from_down, each holding the step number the neighbour has reached.
+    int *d_flags = nullptr;
+    size_t flags_offset = 0;
+    struct Peer {
+        unsigned char *rec = nullptr;  // peer's record array (mapped)
+        int *flags = nullptr;
+        size_t image_stride = 0;
+        int H = 0;
+        void *ipc_base = nullptr;      // non-null when opened with cudaIpcOpenMemHandle
+    } peer[2];                         // 0 = rank above, 1 = rank below
+    int step = 0;                      // prepass count (the protocol's clock)
     unsigned long long *d_trace = nullptr;  // SMC_STREAM_TRACE=<file>: per-CTA timeline of the last streaming launch
 };
 
@@ -91,11 +104,13 @@ static int alloc_records(smc_denoiser *d) {
     d->rec_pitch = ((d->W + 2 * d->padX + 15) / 16) * 16;
     d->rec_rows = d->H + 2 * r + 4;  // +4: rows only ever paired with out-of-range centre rows of the last tile
     d->rec_image_stride = (size_t)d->rec_rows * smc_rec_row_bytes(d->rec_pitch);
-    const size_t bytes = d->rec_image_stride * d->ptr_count;
+    d->flags_offset = ((d->rec_image_stride * d->ptr_count + 255) / 256) * 256;
+    const size_t bytes = d->flags_offset + 256;
     cudaError_t e = cudaMalloc(&d->d_rec, bytes);
     if (e != cudaSuccess)
         SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu bytes of records) failed: %s", bytes, cudaGetErrorString(e));
     SMC_CUDA(cudaMemsetAsync(d->d_rec, 0, bytes, d->ctx->stream));
+    d->d_flags = (int *)(d->d_rec + d->flags_offset);
     return SMC_OK;
 }
 
@@ -274,6 +289,8 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     cudaFree(d->d_gf);
     cudaFree(d->d_sw);
     cudaFree(d->d_rowrange);
+    for (int w = 0; w < 2; w++)
+        if (d->peer[w].ipc_base) cudaIpcCloseMemHandle(d->peer[w].ipc_base);
     cudaFree(d->d_rec);
     cudaFree(d->d_tile_counter);
     for (cudaEvent_t e : d->events) cudaEventDestroy(e);
@@ -299,8 +316,17 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1) {
             p.g_scale[k] = sqrtf(-d->h_gf[g] * 1.4426950408889634f);
         }
     p.mean_corr = d->t_mc; p.disc = d->t_disc; p.lut = d->ctx->d_lut;
+    const size_t row_bytes = smc_rec_row_bytes(d->rec_pitch);
+    const smc_denoiser::Peer &up = d->peer[0], &dn = d->peer[1];
+    // bottom halo of the rank above: its padded rows [H_up + r, H_up + 2r); top halo of the rank below: padded rows [0, r)
+    p.peer_up_halo = up.rec ? up.rec + (size_t)(up.H + d->radius) * row_bytes : nullptr;
+    p.peer_down_halo = dn.rec ? dn.rec : nullptr;
+    p.peer_up_image_stride = up.image_stride;
+    p.peer_down_image_stride = dn.image_stride;
     return smc_launch_prepass(d->ctx, p);
 }
+
+static bool has_peers(const smc_denoiser *d) { return d->peer[0].rec || d->peer[1].rec; }
 
 // filter over output rows [y0, y1)
 static int filter_rows(smc_denoiser *d, int y0, int y1) {
@@ -328,7 +354,18 @@ static int check_rows(const smc_denoiser *d, int y0, int y1, int lo, int hi) {
 
 extern "C" int smc_denoiser_prepass(smc_denoiser *d) {
     if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
-    return prepass_rows(d, 0, d->H);
+    if (!has_peers(d)) return prepass_rows(d, 0, d->H);
+    // Halo protocol, step k: the neighbours must have finished FILTERING step k-1 before their halo rows are overwritten
+    // (they signal free_from_* = k-1 into OUR flags); after the prepass (own records + halo rows stored into the
+    // neighbours' arrays) tell them their halos of step k are ready.
+    d->step++;
+    int rc = smc_launch_halo_wait(d->ctx, d->peer[0].rec ? d->d_flags + 2 : nullptr, d->peer[1].rec ? d->d_flags + 3 : nullptr,
+                                  d->step - 1);
+    if (rc) return rc;
+    if ((rc = prepass_rows(d, 0, d->H))) return rc;
+    // the rank above sees us as "down", the rank below as "up"
+    return smc_launch_halo_signal(d->ctx, d->peer[0].flags ? d->peer[0].flags + 1 : nullptr,
+                                  d->peer[1].flags ? d->peer[1].flags + 0 : nullptr, d->step);
 }
 
 extern "C" int smc_denoiser_prepass_rows(smc_denoiser *d, int row_begin, int row_end) {
@@ -340,7 +377,14 @@ extern "C" int smc_denoiser_prepass_rows(smc_denoiser *d, int row_begin, int row
 
 extern "C" int smc_denoiser_filter(smc_denoiser *d) {
     if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
-    return filter_rows(d, d->row_begin, d->row_end);
+    if (!has_peers(d)) return filter_rows(d, d->row_begin, d->row_end);
+    // wait until both neighbours have stored this step's halo rows into our array, filter, then release their halos
+    int rc = smc_launch_halo_wait(d->ctx, d->peer[0].rec ? d->d_flags + 0 : nullptr, d->peer[1].rec ? d->d_flags + 1 : nullptr,
+                                  d->step);
+    if (rc) return rc;
+    if ((rc = filter_rows(d, d->row_begin, d->row_end))) return rc;
+    return smc_launch_halo_signal(d->ctx, d->peer[0].flags ? d->peer[0].flags + 3 : nullptr,
+                                  d->peer[1].flags ? d->peer[1].flags + 2 : nullptr, d->step);
 }
 
 extern "C" int smc_denoiser_filter_rows(smc_denoiser *d, int row_begin, int row_end) {
@@ -476,6 +520,76 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
     if (!e_end) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
     SMC_CUDA(cudaEventRecord(e_end, d->s_out));
     SMC_CUDA(cudaStreamWaitEvent(ctx->stream, e_end, 0));
+    return SMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Peer halos: the multi-GPU exchange as stores into the neighbours' record arrays (see smc_prepass.cu)
+// ---------------------------------------------------------------------------------------------------------
+static int peer_check(smc_denoiser *d, int which, int peer_H, int peer_radius, int peer_pitch, int peer_pc) {
+    if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
+    if (which != 0 && which != 1) SMC_FAIL(SMC_ERR_INVALID, "which must be 0 (rank above) or 1 (rank below)");
+    if (which == 0 ? !d->skip_top : !d->skip_bottom)
+        SMC_FAIL(SMC_ERR_INVALID, "the plan was not created with halo_%s_external", which == 0 ? "top" : "bottom");
+    if (peer_radius != d->radius || peer_pitch != d->rec_pitch || peer_pc != d->ptr_count)
+        SMC_FAIL(SMC_ERR_INVALID, "peer plan has a different radius / width / image count");
+    if (peer_H < d->radius || d->H < d->radius)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "bands (%d and %d rows) must be at least `radius` = %d rows", d->H, peer_H, d->radius);
+    if (d->peer[which].rec) SMC_FAIL(SMC_ERR_INVALID, "peer %d already attached", which);
+    return SMC_OK;
+}
+
+extern "C" int smc_denoiser_peer_export(smc_denoiser *d, smc_peer_info *out) {
+    if (!d || !out) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    SMC_CUDA(cudaSetDevice(d->ctx->device));
+    cudaIpcMemHandle_t h;
+    SMC_CUDA(cudaIpcGetMemHandle(&h, d->d_rec));
+    static_assert(sizeof(h) == sizeof(out->ipc_handle), "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out->ipc_handle, &h, sizeof(h));
+    out->image_stride = d->rec_image_stride;
+    out->flags_offset = d->flags_offset;
+    out->height = d->H; out->radius = d->radius; out->rec_pitch = d->rec_pitch; out->ptr_count = d->ptr_count;
+    out->device = d->ctx->device;
+    return SMC_OK;
+}
+
+extern "C" int smc_denoiser_peer_attach(smc_denoiser *d, int which, const smc_peer_info *info) {
+    if (!info) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    int rc = peer_check(d, which, info->height, info->radius, info->rec_pitch, info->ptr_count);
+    if (rc) return rc;
+    SMC_CUDA(cudaSetDevice(d->ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, info->ipc_handle, sizeof(h));
+    void *base = nullptr;
+    SMC_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    smc_denoiser::Peer &p = d->peer[which];
+    p.ipc_base = base;
+    p.rec = (unsigned char *)base;
+    p.flags = (int *)((unsigned char *)base + info->flags_offset);
+    p.image_stride = info->image_stride;
+    p.H = info->height;
+    return SMC_OK;
+}
+
+extern "C" int smc_denoiser_peer_attach_local(smc_denoiser *d, int which, smc_denoiser *other) {
+    if (!other) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    int rc = peer_check(d, which, other->H, other->radius, other->rec_pitch, other->ptr_count);
+    if (rc) return rc;
+    if (other->ctx->device != d->ctx->device) {
+        SMC_CUDA(cudaSetDevice(d->ctx->device));
+        int can = 0;
+        SMC_CUDA(cudaDeviceCanAccessPeer(&can, d->ctx->device, other->ctx->device));
+        if (!can) SMC_FAIL(SMC_ERR_UNSUPPORTED, "device %d cannot access device %d", d->ctx->device, other->ctx->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SMC_CUDA(e);
+        cudaGetLastError();
+    }
+    smc_denoiser::Peer &p = d->peer[which];
+    p.rec = other->d_rec;
+    p.flags = other->d_flags;
+    p.image_stride = other->rec_image_stride;
+    p.H = other->H;
     return SMC_OK;
 }
 

@@ -125,6 +125,11 @@ struct SmcPrepassParams {
     unsigned char *rec;
     int skip_top, skip_bottom;  // halo rows filled externally
     int pr_begin, pr_end;       // padded record rows [pr_begin, pr_end) to produce (padded row pr holds y = pr - radius)
+    // Peer halos (multi-GPU): when set, the records of the top / bottom `radius` own rows are ALSO stored straight into the
+    // neighbouring rank's record array over NVLink (peer-mapped memory): into the bottom halo of the rank above
+    // (its padded rows [H_up + r, H_up + 2r)) and the top halo of the rank below (its padded rows [0, r)).
+    unsigned char *peer_up_halo, *peer_down_halo;   // address of the first halo row of image 0 in the peer's array, or null
+    size_t peer_up_image_stride, peer_down_image_stride;
     const SmcPtrStepSz *n, *mean, *m2, *m3, *film_ptrs;
     SmcPtrStepSz film;
     const SmcPtrStepSz *gbufs;           // G-buffer plane descriptors (device table)
@@ -138,6 +143,8 @@ struct SmcPrepassParams {
 };
 
 int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p);
+int smc_launch_halo_signal(smc_context *ctx, int *f0, int *f1, int value);
+int smc_launch_halo_wait(smc_context *ctx, const int *f0, const int *f1, int value);
 int smc_launch_filter_generic(smc_context *ctx, const SmcFilterParams &p);
 // returns SMC_ERR_UNSUPPORTED when the configuration has no streaming instantiation.
 // rowrange: device array, one {jlo, jhi} per spatial-table row; py: output rows per thread (2 or 4)

@@ -147,10 +147,44 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
 #pragma unroll
     for (int k = 0; k < NG; k++) rec[slots[k]] = __fmul_rn(g[k], p.g_scale[k]);
 
-    unsigned char *row = p.rec + (size_t)z * p.rec_image_stride + (size_t)pr * smc_rec_row_bytes(p.rec_pitch);
+    const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
+    unsigned char *row = p.rec + (size_t)z * p.rec_image_stride + (size_t)pr * row_bytes;
 #pragma unroll
     for (int c = 0; c < 4; c++)
         *(float4 *)(row + smc_rec_chunk_offset(pc, c)) = make_float4(rec[4 * c], rec[4 * c + 1], rec[4 * c + 2], rec[4 * c + 3]);
+    // halo exchange fused into the producer: the same record goes to the neighbouring GPUs that need it (peer stores)
+    if (yy == y) {
+        unsigned char *peer = nullptr;
+        if (p.peer_up_halo && yy < p.radius) peer = p.peer_up_halo + (size_t)z * p.peer_up_image_stride + (size_t)yy * row_bytes;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (peer) *(float4 *)(peer + smc_rec_chunk_offset(pc, c)) = make_float4(rec[4 * c], rec[4 * c + 1], rec[4 * c + 2], rec[4 * c + 3]);
+        peer = nullptr;
+        if (p.peer_down_halo && yy >= p.H - p.radius)
+            peer = p.peer_down_halo + (size_t)z * p.peer_down_image_stride + (size_t)(yy - (p.H - p.radius)) * row_bytes;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (peer) *(float4 *)(peer + smc_rec_chunk_offset(pc, c)) = make_float4(rec[4 * c], rec[4 * c + 1], rec[4 * c + 2], rec[4 * c + 3]);
+    }
+}
+
+// Cross-GPU flags of the halo protocol: a release store at system scope after everything this stream did before, and a
+// spinning acquire load (one thread; the waiting GPU has nothing else to do on that stream).
+__global__ void halo_signal_kernel(int *f0, int *f1, int value) {
+    __threadfence_system();
+    if (f0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f0), "r"(value) : "memory");
+    if (f1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f1), "r"(value) : "memory");
+}
+__global__ void halo_wait_kernel(const int *f0, const int *f1, int value) {
+    for (int k = 0; k < 2; k++) {
+        const int *f = k ? f1 : f0;
+        if (!f) continue;
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v < value) __nanosleep(200);
+        } while (v < value);
+    }
 }
 
 }  // namespace
@@ -167,6 +201,19 @@ static void launch_prepass_ng(const SmcPrepassParams &p, dim3 grid, dim3 block, 
         case 6: prepass_kernel<C, 6><<<grid, block, 0, s>>>(p); break;
         default: prepass_kernel<C, 7><<<grid, block, 0, s>>>(p); break;
     }
+}
+
+int smc_launch_halo_signal(smc_context *ctx, int *f0, int *f1, int value) {
+    if (!f0 && !f1) return SMC_OK;
+    halo_signal_kernel<<<1, 1, 0, ctx->stream>>>(f0, f1, value);
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
+}
+int smc_launch_halo_wait(smc_context *ctx, const int *f0, const int *f1, int value) {
+    if (!f0 && !f1) return SMC_OK;
+    halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(f0, f1, value);
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
 }
 
 int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p) {

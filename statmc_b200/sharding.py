@@ -43,3 +43,16 @@ def exchange_halos(dist, rank: int, world: int, own_top, own_bottom, halo_above,
         return
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+def attach_peers(dist, rank: int, world: int, denoiser) -> None:
+    """Peer-halo mode: every rank publishes its record array (CUDA IPC handle, 128 bytes) and maps its neighbours'.
+    After this, Denoiser.prepass() stores the edge records into the neighbours' halo rows itself and prepass / filter
+    synchronise through device flags: there is no exchange call in the step."""
+    infos = [None] * world
+    dist.all_gather_object(infos, denoiser.peer_export())
+    if rank > 0:
+        denoiser.peer_attach(0, infos[rank - 1])
+    if rank < world - 1:
+        denoiser.peer_attach(1, infos[rank + 1])
+    dist.barrier()

@@ -259,3 +259,39 @@ def test_host_pipelined_run_is_exact(ctx, kernel, chunk):
         assert bits_equal(h_out.array, ref["film_f"]), (kernel, chunk, rep)
         assert bits_equal(h_mc.array, ref["mean_corr"]) and bits_equal(h_dc.array, ref["disc"])
     dn.close()
+
+
+def test_peer_halo_mode(ctx):
+    # two "ranks" as two plans in one process: the prepass of each stores its edge records straight into the other's halo
+    # rows (the multi-GPU path, smc_denoiser_peer_attach_local); flags order prepass / filter across the two; two steps with
+    # different inputs check that a step's halos are not overwritten early and not reused late
+    W, H, r, sd = 300, 64, 10, 5.0
+    plans = []
+    for gidx in range(2):
+        y0, y1 = gidx * H // 2, (gidx + 1) * H // 2
+        dev = {k: Buffer(ctx, y1 - y0, W, 1 if k == "n" else 3, np.int32 if k == "n" else np.float32)
+               for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
+        out = Buffer(ctx, y1 - y0, W, 3)
+        dn = Denoiser(ctx, channels=3, width=W, height=y1 - y0, radius=r, ds_factor=-0.5 / sd ** 2, n=[dev["n"]],
+                      mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]], film=dev["film"],
+                      gbufs=[dev["normal"], dev["albedo"]], gbuf_dr_factors=[-0.5 / 0.01, -0.5 / 0.0004],
+                      film_filtered_ptrs=[out], film_filtered=out, denoise_film=True, kernel=2,
+                      halo_top_external=(gidx == 1), halo_bottom_external=(gidx == 0))
+        plans.append((dn, out, dev, y0, y1))
+    plans[0][0].peer_attach_local(1, plans[1][0])
+    plans[1][0].peer_attach_local(0, plans[0][0])
+    for step, cfg in enumerate((52, 53)):
+        b = synth.moment_buffers(W, H, n=32, config_id=cfg)
+        full = denoise_host(ctx, b, radius=r, sd=sd, kernel=2)["film_f"]
+        for dn, out, dev, y0, y1 in plans:
+            for k, buf in dev.items():
+                buf.upload(np.ascontiguousarray(b[k][y0:y1]))
+        for dn, *_ in plans:
+            dn.prepass()
+        for dn, *_ in plans:
+            dn.filter()
+        ctx.synchronize()
+        got = np.concatenate([plans[0][1].download(), plans[1][1].download()], axis=0)
+        assert bits_equal(got, full), step
+    for dn, *_ in plans:
+        dn.close()
