@@ -422,8 +422,9 @@ static int auto_chunk_rows(const smc_denoiser *d) {
         // whole waves of the persistent grid per chunk: tiles(chunk) = k * grid, about 8 chunks per frame
         SmcFilterParams p;
         fill_filter_params(d, p);
-        const int grid = smc_filter_stream_resident_ctas(p, d->py, d->ctx->sm_count);
-        const int tiles_x = (d->W + 255) / 256;
+        int tile_w = 256;
+        const int grid = smc_filter_stream_resident_ctas(p, d->py, d->ctx->sm_count, &tile_w);
+        const int tiles_x = (d->W + tile_w - 1) / tile_w;
         const long long total = (long long)tiles_x * ((rows + d->py - 1) / d->py);
         long long k = (total / std::max(grid, 1) + 4) / 8;
         if (k < 1) k = 1;

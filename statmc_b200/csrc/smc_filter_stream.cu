@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "smc_filter_math.cuh"
 #include "smc_internal.h"
@@ -338,6 +339,248 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-warp streaming variant.  Same per-pair arithmetic and the same 2 x PY pixels per thread, but every WARP is an
+// independent worker: it owns a 64 x PY tile, a private two-slot ring of record rows (64 + 2r records wide, filled by
+// its own 1-D bulk copies) and its own tile sequence drawn from the global counter.  Nothing couples the warps of a
+// CTA after the start-up barrier: no shared ring (in the CTA-wide kernel a warp that runs ahead blocks on the slot
+// the slowest warp still reads: 10 % of all warp samples sat in that wait, ncu r1b), no per-row shared atomics, and
+// the per-row bookkeeping is a few integer instructions (slot = row parity; no divisions).  One CTA per SM holds as
+// many warps as registers (168 per thread -> 12) and shared memory allow and shares one copy of the spatial table.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWTileW = 64;
+constexpr int kWMaxThreads = 384;
+
+struct WarpGeom {
+    int tiles_x, tiles_y, total_tiles;
+    int nr;            // record rows per tile = 2r + PY - 1
+    int slot_bytes;    // bytes per ring slot (multiple of 128)
+    int seg_max_rec;   // records per full segment (even)
+    int sw_rows;
+    int nwarps;        // warps per CTA
+    const int2 *rowrange;
+};
+
+struct WTile {
+    int z, x0, y0;
+    const unsigned char *src0;  // first record row of the tile's segment
+    uint32_t bytes;             // bytes per row segment
+};
+
+__device__ __forceinline__ WTile wtile_make(int t, const SmcFilterParams &p, const WarpGeom &g, int PY) {
+    WTile w;
+    const int per_img = g.tiles_x * g.tiles_y;
+    w.z = t / per_img;
+    const int rem = t - w.z * per_img;
+    const int ty = rem / g.tiles_x;
+    w.x0 = (rem - ty * g.tiles_x) * kWTileW;
+    w.y0 = p.row_begin + ty * PY;
+    const int seg_start = seg_start_of(p, w.x0);
+    const int nrec = min(g.seg_max_rec, p.rec_pitch - seg_start);  // even
+    w.src0 = p.rec + (size_t)w.z * p.rec_image_stride + (size_t)w.y0 * smc_rec_row_bytes(p.rec_pitch) +
+             smc_rec_offset(seg_start);
+    w.bytes = (uint32_t)(nrec / 2) * SMC_LINE_BYTES;
+    return w;
+}
+
+template <int NG, int PY, int MODE, bool COUNT>
+__global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcFilterParams p, const WarpGeom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [rings: nwarps x 2 x slot_bytes][sw table][rowrange][barriers: nwarps x 2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = smem + (size_t)warp * 2 * g.slot_bytes;
+    float *sw = (float *)(smem + (size_t)g.nwarps * 2 * g.slot_bytes);
+    int2 *rowrange = (int2 *)(sw + g.sw_rows * p.sw_stride);
+    uint64_t *full = (uint64_t *)(rowrange + g.sw_rows) + 2 * warp;
+
+    for (int i = threadIdx.x; i < g.sw_rows * p.sw_stride; i += blockDim.x) sw[i] = p.sw[i];
+    for (int i = threadIdx.x; i < g.sw_rows; i += blockDim.x) rowrange[i] = g.rowrange[i];
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide synchronisation
+
+    const int r = p.radius;
+    const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
+    const int total_warps = (int)gridDim.x * g.nwarps;
+    // warps that run side by side start on neighbouring tiles: the rows they share come out of L2
+    int t_cur = (int)blockIdx.x * g.nwarps + warp;
+    if (t_cur >= g.total_tiles) return;
+    WTile ti = wtile_make(t_cur, p, g, PY);
+    const uint32_t full0 = smem_u32(&full[0]);
+    const uint32_t ring0 = smem_u32(ring);
+    auto issue = [&](const unsigned char *src, uint32_t bytes, int s) {  // lane 0 only
+        const uint32_t bar = full0 + 8u * (uint32_t)s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ring0 + (uint32_t)s * (uint32_t)g.slot_bytes),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+        issue(ti.src0, ti.bytes, 0);
+        issue(ti.src0 + row_bytes, ti.bytes, 1);  // nr >= 3
+    }
+
+    uint32_t pos = 0;  // rows consumed so far: slot = pos & 1, phase parity = (pos >> 1) & 1
+    for (;;) {
+        // the tile after this one: asked for now, first needed two rows before the end of the tile
+        int nxt_raw = 0;
+        if (lane == 0) nxt_raw = total_warps + atomicAdd(p.tile_counter, 1);  // ~1 us, once per ~350 us tile
+        int t_next = g.total_tiles;
+        WTile tn = ti;
+
+        const unsigned char *img = p.rec + (size_t)ti.z * p.rec_image_stride;
+        const int xf = ti.x0 + 2 * lane;  // first of this thread's two columns
+        const int base_idx = xf + p.padX - seg_start_of(p, ti.x0);  // slot index of the record at dx = 0, column kx = 0
+
+        SmcCentre<3, NG> cen[PY][2];
+        Acc acc[PY][2];
+#pragma unroll
+        for (int ky = 0; ky < PY; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+                const int yc = min(ti.y0 + ky, p.H - 1), xc = min(xf + kx, p.W - 1);
+                const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, xc + p.padX);
+                smc_make_centre<3, NG, MODE>(rc, cen[ky][kx]);
+                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = 0.f;
+                acc[ky][kx].cnt = 0;
+            }
+
+        for (int i = 0; i < g.nr; i++, pos++) {
+            const int s = (int)(pos & 1u);
+            {
+                const uint32_t bar = full0 + 8u * (uint32_t)s, parity = (pos >> 1) & 1u;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "WWAIT_LOOP:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra WDONE;\n"
+                    "bra WWAIT_LOOP;\n"
+                    "WDONE:\n"
+                    "}\n" ::"r"(bar),
+                    "r"(parity)
+                    : "memory");
+            }
+            {
+                // table row of centre row ky: dy = i - r - ky  ->  row index i - ky + margin_y
+                int lo = 1 << 20, hi = -(1 << 20);
+#pragma unroll
+                for (int ky = 0; ky < PY; ky++) {
+                    const int2 rr = rowrange[i - ky + p.sw_margin_y];
+                    lo = min(lo, rr.x);
+                    hi = max(hi, rr.y);
+                }
+                if (lo <= hi) {
+                    const float *swp = sw + (i + p.sw_margin_y) * p.sw_stride + (r + p.sw_margin_x) + lo;
+                    const int sws = p.sw_stride;
+                    float sw_prev[PY];
+#pragma unroll
+                    for (int ky = 0; ky < PY; ky++) sw_prev[ky] = swp[-ky * sws - 1];
+                    const int first = base_idx + lo;
+                    const unsigned char *rp = ring + (size_t)s * g.slot_bytes + smc_rec_offset(first);
+                    const int d0 = (first & 1) ? SMC_LINE_BYTES - SMC_REC_BYTES : SMC_REC_BYTES;
+                    SmcRec cur = lds_rec(rp);
+                    int j = lo;
+                    for (; j + 1 <= hi; j += 2) {
+                        const SmcRec nxt = lds_rec(rp + d0);
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);       // dx = j
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);  // dx = j - 1
+                            sw_prev[ky] = sw_cur;
+                        }
+                        rp += SMC_LINE_BYTES;
+                        cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws + 1];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], nxt, sw_cur, acc[ky][0]);       // dx = j + 1
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], nxt, sw_prev[ky], acc[ky][1]);  // dx = j
+                            sw_prev[ky] = sw_cur;
+                        }
+                        swp += 2;
+                    }
+                    if (j <= hi) {
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);
+                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // every lane has read the slot
+            if (i == g.nr - 2) {  // the next tile's first row goes into this slot
+                t_next = __shfl_sync(0xffffffffu, nxt_raw, 0);
+                if (t_next < g.total_tiles) tn = wtile_make(t_next, p, g, PY);
+            }
+            if (lane == 0) {
+                const int ii = i + 2;
+                if (ii < g.nr) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(ti.src0 + (size_t)ii * row_bytes, ti.bytes, s);
+                } else if (t_next < g.total_tiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(tn.src0 + (size_t)(ii - g.nr) * row_bytes, tn.bytes, s);
+                }
+            }
+        }
+
+        // write the tile (stat_denoiser.cu:341-344); centre fix-up as in the CTA-wide kernel
+        const SmcPtrStepSz o = (p.denoise_film && ti.z == 0) ? p.film_filtered : p.out_ptrs[ti.z];
+#pragma unroll
+        for (int ky = 0; ky < PY; ky++) {
+            const int y = ti.y0 + ky;
+            if (y >= p.row_end) continue;
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+                const int x = xf + kx;
+                if (x >= p.W) continue;
+                Acc a = acc[ky][kx];
+                const SmcRec rc = ldg_rec(img + (size_t)(y + r) * row_bytes, x + p.padX);
+                if (!smc_member<3, NG, MODE>(cen[ky][kx], rc)) {
+                    a.n0 = __fadd_rn(a.n0, rc.c2.x);
+                    a.n1 = __fadd_rn(a.n1, rc.c2.y);
+                    a.n2 = __fadd_rn(a.n2, rc.c1.z);
+                    a.den = __fadd_rn(a.den, 1.f);
+                    a.cnt += 1;
+                }
+                float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
+                op[0] = __fdiv_rn(a.n0, a.den);
+                op[1] = __fdiv_rn(a.n1, a.den);
+                op[2] = __fdiv_rn(a.n2, a.den);
+                if (COUNT && p.accepted && p.accepted[ti.z].data)
+                    ((int *)(p.accepted[ti.z].data + (size_t)y * p.accepted[ti.z].step))[x] = a.cnt;
+            }
+        }
+        if (t_next >= g.total_tiles) break;
+        t_cur = t_next;
+        ti = tn;
+    }
+}
+
+template <typename K>
+int launch_wk(smc_context *ctx, K k, const SmcFilterParams &p, const WarpGeom &g, size_t smem) {
+    SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<long long>((g.total_tiles + g.nwarps - 1) / g.nwarps, (long long)ctx->sm_count);
+    SMC_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), ctx->stream));
+    k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
+}
+
+template <int NG, int MODE>
+int launch_w(smc_context *ctx, const SmcFilterParams &p, const WarpGeom &g, size_t smem) {
+    if (p.accepted != nullptr) return launch_wk(ctx, filter_warp_kernel<NG, 2, MODE, true>, p, g, smem);
+    return launch_wk(ctx, filter_warp_kernel<NG, 2, MODE, false>, p, g, smem);
+}
+
 template <typename K>
 int launch_k(smc_context *ctx, K k, const SmcFilterParams &p, const StreamGeom &g, size_t smem, int *query_per_sm) {
     SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -407,6 +650,40 @@ static bool stream_geometry(const SmcFilterParams &p, int PY, StreamGeom &g, siz
     return smem <= 220 * 1024;
 }
 
+// geometry of the per-warp variant: one CTA per SM with as many warps as shared memory allows (at most 12: registers)
+static bool warp_geometry(const SmcFilterParams &p, int PY, WarpGeom &g, size_t &smem) {
+    const int rows = p.row_end - p.row_begin;
+    g.tiles_x = (p.W + kWTileW - 1) / kWTileW;
+    g.tiles_y = (rows + PY - 1) / PY;
+    const long long total = (long long)g.tiles_x * g.tiles_y * p.ptr_count;
+    if (total <= 0 || total > 0x3fffffffLL) return false;
+    g.total_tiles = (int)total;
+    g.nr = 2 * p.radius + PY - 1;
+    if (g.nr < 3) return false;
+    g.seg_max_rec = kWTileW + 2 * p.radius + 4;
+    g.slot_bytes = (((g.seg_max_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
+    g.sw_rows = 2 * p.radius + 2 * p.sw_margin_y;
+    const size_t tables = (size_t)g.sw_rows * p.sw_stride * 4 + (size_t)g.sw_rows * 8;
+    const size_t avail = 227 * 1024 - 1024;
+    if (tables + 64 >= avail) return false;
+    int nw = (int)((avail - tables) / (2 * (size_t)g.slot_bytes + 16));
+    if (const char *e = getenv("SMC_WARP_NWARPS")) nw = std::min(nw, atoi(e));  // tuning knob
+    g.nwarps = std::min(nw, kWMaxThreads / 32);
+    smem = (size_t)g.nwarps * 2 * g.slot_bytes + tables + (size_t)g.nwarps * 16;
+    return g.nwarps >= 4;
+}
+
+// which streaming variant: per-warp rings (default when they fit) or the CTA-wide ring; SMC_STREAM_KERNEL=cta|warp
+static bool use_warp_variant(const SmcFilterParams &p, int py) {
+    if (py != 2) return false;
+    if (const char *e = getenv("SMC_STREAM_KERNEL")) {
+        if (!strcmp(e, "cta")) return false;
+    }
+    WarpGeom g;
+    size_t smem = 0;
+    return warp_geometry(p, 2, g, smem);
+}
+
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name) {
     (void)sm_count;
     if (p.C != 3) return false;
@@ -429,7 +706,15 @@ int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const i
     return stream_dispatch(ctx, p, d_rowrange, py, name, nullptr);
 }
 
-int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count) {
+int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count, int *tile_w) {
+    if (use_warp_variant(p, py)) {
+        WarpGeom g;
+        size_t smem = 0;
+        warp_geometry(p, 2, g, smem);
+        if (tile_w) *tile_w = kWTileW;
+        return g.nwarps * sm_count;
+    }
+    if (tile_w) *tile_w = kTileW;
     int per_sm = 0;
     if (stream_dispatch(nullptr, p, nullptr, py, nullptr, &per_sm) != SMC_OK || per_sm < 1) per_sm = 1;
     return per_sm * sm_count;
@@ -438,6 +723,23 @@ int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_cou
 static int stream_dispatch(smc_context *ctx, const SmcFilterParams &p, const int2 *d_rowrange, int py,
                            const char **name, int *query_per_sm) {
     int *q = query_per_sm;
+    if (!q && use_warp_variant(p, py)) {
+        WarpGeom wg;
+        size_t wsmem = 0;
+        warp_geometry(p, 2, wg, wsmem);
+        wg.rowrange = d_rowrange;
+        static thread_local char wnm[64];
+        snprintf(wnm, sizeof(wnm), "stream-warp<NG=%d,PY=2,%s,W=%d>", p.NG, p.mode ? "moon" : "welch", wg.nwarps);
+        if (name) *name = wnm;
+        switch (p.NG) {
+            case 0: return p.mode == 0 ? launch_w<0, 0>(ctx, p, wg, wsmem) : launch_w<0, 1>(ctx, p, wg, wsmem);
+            case 3: return p.mode == 0 ? launch_w<3, 0>(ctx, p, wg, wsmem) : launch_w<3, 1>(ctx, p, wg, wsmem);
+            case 6: return p.mode == 0 ? launch_w<6, 0>(ctx, p, wg, wsmem) : launch_w<6, 1>(ctx, p, wg, wsmem);
+            case 7: return p.mode == 0 ? launch_w<7, 0>(ctx, p, wg, wsmem) : launch_w<7, 1>(ctx, p, wg, wsmem);
+            default: break;
+        }
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: NG=%d not instantiated", p.NG);
+    }
     StreamGeom g;
     size_t smem = 0;
     if (!stream_geometry(p, py, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: geometry not supported");

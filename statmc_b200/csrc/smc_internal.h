@@ -150,8 +150,9 @@ int smc_launch_filter_generic(smc_context *ctx, const SmcFilterParams &p);
 // rowrange: device array, one {jlo, jhi} per spatial-table row; py: output rows per thread (2 or 4)
 int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *rowrange, int py,
                              const char **name);
-// CTAs of the persistent streaming grid that are resident at once (occupancy x SM count)
-int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count);
+// workers (CTAs, or warps for the per-warp variant) of the persistent streaming grid that are resident at once, and
+// the width in pixels of the tile one worker owns
+int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count, int *tile_w);
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name);
 #define SMC_SW_MARGIN_Y 3
 #define SMC_SW_MARGIN_X 2
