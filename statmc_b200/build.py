@@ -88,6 +88,24 @@ def build_cpp_tests() -> str:
     return out
 
 
+def build_cli() -> str:
+    """g++ build of the denoise-replay program statmc_b200/cli/smc_denoise.cpp (the reference's `pbrt --denoise` flow over
+    PFM dumps, statpath.cpp:455-550) into build/smc_denoise."""
+    src = os.path.join(ROOT, "statmc_b200", "cli", "smc_denoise.cpp")
+    out = os.path.join(ROOT, "build", "smc_denoise")
+    inc = os.path.join(ROOT, "include")
+    deps = [src, LIB] + [os.path.join(inc, h) for h in ("statmc_b200.hpp", "statmc_b200.h", "statmc_pfm.hpp")]
+    if _newer(out, deps):
+        return out
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-I", inc, src, "-o", out,
+           "-L", os.path.join(ROOT, "statmc_b200"), "-lstatmc_b200", "-Wl,-rpath,$ORIGIN/../statmc_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for smc_denoise.cpp:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build_variant(name: str, defines: list[str]) -> str:
     """Experiment builds: statmc_b200/libstatmc_b200_<name>.so compiled with extra -D flags (A/B timing only;
     select with the environment variable SMC_LIB_VARIANT=<name>)."""

@@ -13,7 +13,7 @@ B="python bench.py --no-cpu-baseline --no-e2e"
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$R.csv $B --steps 2 --warmup 3 > gpurun_out/ncu_list.log 2>&1; echo "rc=$?"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_stream -s 3 -c 1 -f -o gpurun_out/prof_filter_$R $B --no-accum --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_ -s 3 -c 1 -f -o gpurun_out/prof_filter_$R $B --no-accum --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:prepass -s 3 -c 1 -f -o gpurun_out/prof_prepass_$R $B --no-accum --steps 1 --warmup 3 > gpurun_out/ncu_full2.log 2>&1; tail -2 gpurun_out/ncu_full2.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:accumulate -s 2 -c 1 -f -o gpurun_out/prof_accum_$R $B --steps 1 --warmup 3 > gpurun_out/ncu_full3.log 2>&1; tail -2 gpurun_out/ncu_full3.log
 ls -la gpurun_out
