@@ -89,7 +89,7 @@ class RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def cpu_baseline(W, radius, sd, n, seconds_target=12.0):
+def cpu_baseline(W, H, radius, sd, n, seconds_target=12.0):
     """The oracle port (CPU restatement of the reference kernels, OpenMP over all host cores) on a bounded sample:
     a full-width band of rows of the same workload.  Reported as baseline only."""
     from oracle import pyoracle as po
@@ -103,7 +103,7 @@ def cpu_baseline(W, radius, sd, n, seconds_target=12.0):
     dt = time.perf_counter() - t0
     px = W * (rows + 2 * radius)
     # one more, scaled to the time target, for a steadier number
-    rows2 = int(max(rows, min(4 * (rows + 2 * radius), (rows + 2 * radius) * seconds_target / max(dt, 1e-3))))
+    rows2 = int(max(rows, min(H, (rows + 2 * radius) * seconds_target / max(dt, 1e-3))))
     b = synth.moment_buffers(W, rows2, n=n, config_id=3)
     t0 = time.perf_counter()
     po.denoise(b, radius=radius, sd=sd)
@@ -128,11 +128,16 @@ def main():
                          "(peer-mapped memory, device flags; default); exchange = NCCL send/recv of record halos; "
                          "redundant = carry raw halo rows per band, no device-to-device traffic")
     ap.add_argument("--gbufs", type=int, default=2, help="experiments: 0 = no G-buffers, 1 = normal only, 2 = normal + albedo")
+    ap.add_argument("--channels", type=int, default=3, choices=[1, 3],
+                    help="experiments: 1 = scalar statistics (multichannelstats=false): luminance moments gate the filter of the "
+                         "scalar film-mean AND of the RGB film (stat_denoiser.cu:208-274); device-resident timing only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-accum", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.channels == 1:
+        args.no_e2e = args.no_accum = args.no_cpu_baseline = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,10 +184,15 @@ def main():
     dev = {k: Buffer(ctx, rows, W, 1 if bufs[k].ndim == 2 else 3, bufs[k].dtype, k) for k in names}
     out = Buffer(ctx, rows, W, 3, np.float32, "film-f")
     out_host = PinnedArray((y1 - y0, W, 3), np.float32)
-    dn = Denoiser(ctx, channels=3, width=W, height=rows, radius=radius, ds_factor=-0.5 / (sd * sd),
-                  n=[dev["n"]], mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]],
+    stat, out_ptrs = dev, [out]
+    if args.channels == 1:  # luminance-like scalar statistics: channel 1 of the RGB planes
+        stat = {k: Buffer.from_array(ctx, np.ascontiguousarray(bufs[k][..., 1]), k) for k in ("mean", "m2", "m3", "film")}
+        stat["n"] = dev["n"]
+        out_ptrs = [Buffer(ctx, rows, W, 1, np.float32, "t0-b0-film-mean-f")]
+    dn = Denoiser(ctx, channels=args.channels, width=W, height=rows, radius=radius, ds_factor=-0.5 / (sd * sd),
+                  n=[stat["n"]], mean=[stat["mean"]], m2=[stat["m2"]], m3=[stat["m3"]], film_ptrs=[stat["film"]],
                   film=dev["film"], gbufs=[dev["normal"], dev["albedo"]][:args.gbufs],
-                  gbuf_dr_factors=[-0.5 / NORMAL_SD ** 2, -0.5 / ALBEDO_SD ** 2][:args.gbufs], film_filtered_ptrs=[out],
+                  gbuf_dr_factors=[-0.5 / NORMAL_SD ** 2, -0.5 / ALBEDO_SD ** 2][:args.gbufs], film_filtered_ptrs=out_ptrs,
                   film_filtered=out, denoise_film=True, row_begin=y0 - lo, row_end=y1 - lo, kernel=args.kernel,
                   halo_top_external=exchange and rank > 0, halo_bottom_external=exchange and rank < world - 1)
 
@@ -377,7 +387,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "accum": accum,
         }
         if world == 1 and not args.no_cpu_baseline:
-            res["cpu_baseline"] = cpu_baseline(W, radius, sd, n)
+            res["cpu_baseline"] = cpu_baseline(W, H, radius, sd, n)
         print(json.dumps(res), flush=True)
     dn.close()
     if world > 1:
@@ -407,7 +417,7 @@ def reference_arm(args, local):
     except Exception:
         has_gpu = False
     if not has_gpu:
-        cb = cpu_baseline(W, radius, sd, n, seconds_target=20.0)
+        cb = cpu_baseline(W, H, radius, sd, n, seconds_target=20.0)
         base.update({"value": cb["value"], "ms_per_step": W * H / cb["value"] / 1e3, "config": cfg, "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         print(json.dumps(base), flush=True)

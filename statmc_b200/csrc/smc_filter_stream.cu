@@ -101,6 +101,7 @@ __device__ __forceinline__ SmcRec ldg_rec(const unsigned char *row, int pcol) {
 
 struct Acc {
     float n0, n1, n2, den;
+    float ns;  // scalar statistics only: the scalar value's sum
     int cnt;
 };
 
@@ -114,6 +115,25 @@ __device__ __forceinline__ void pair_eval(const SmcCentre<3, NG> &c, const SmcRe
         a.n2 = __fmaf_rn(w, r.c1.z, a.n2);
         a.den = __fadd_rn(a.den, w);
         // a tap outside the window has sw = -inf -> w = 0: it adds nothing, but must not be counted
+        if (COUNT) a.cnt += (sw != -INFINITY) ? 1 : 0;
+    }
+}
+
+// Per-warp kernel: C = channels of the statistics (1 or 3).  C == 3 averages the RGB value (slots 8, 9, 6).  C == 1 averages the
+// scalar value (slot 4) and, for the image that also filters the film (denoiseFilm, z == 0; stat_denoiser.cu:251-253,
+// :263-265), the film RGB as well (FILM).
+template <int C, int NG, int MODE, bool COUNT, bool FILM>
+__device__ __forceinline__ void pair_eval_c(const SmcCentre<C, NG> &c, const SmcRec &r, float sw, Acc &a) {
+    const bool ok = smc_member<C, NG, MODE>(c, r);
+    const float w = smc_weight<C, NG>(c, r, sw);
+    if (ok) {
+        if (C == 3 || FILM) {
+            a.n0 = __fmaf_rn(w, r.c2.x, a.n0);
+            a.n1 = __fmaf_rn(w, r.c2.y, a.n1);
+            a.n2 = __fmaf_rn(w, r.c1.z, a.n2);
+        }
+        if (C == 1) a.ns = __fmaf_rn(w, r.c1.x, a.ns);
+        a.den = __fadd_rn(a.den, w);
         if (COUNT) a.cnt += (sw != -INFINITY) ? 1 : 0;
     }
 }
@@ -383,7 +403,64 @@ __device__ __forceinline__ WTile wtile_make(int t, const SmcFilterParams &p, con
     return w;
 }
 
-template <int NG, int PY, int MODE, bool COUNT>
+// One record row (already in the warp's ring slot) against the warp's 2 x PY centre pixels per lane.
+template <int C, int NG, int PY, int MODE, bool COUNT, bool FILM>
+__device__ __forceinline__ void warp_row(const SmcFilterParams &p, const SmcCentre<C, NG> (&cen)[PY][2], Acc (&acc)[PY][2],
+                                         const int2 *rowrange, const float *sw, const unsigned char *slot, int i, int base_idx) {
+    const int r = p.radius;
+    {
+                // table row of centre row ky: dy = i - r - ky  ->  row index i - ky + margin_y
+                int lo = 1 << 20, hi = -(1 << 20);
+#pragma unroll
+                for (int ky = 0; ky < PY; ky++) {
+                    const int2 rr = rowrange[i - ky + p.sw_margin_y];
+                    lo = min(lo, rr.x);
+                    hi = max(hi, rr.y);
+                }
+                if (lo <= hi) {
+                    const float *swp = sw + (i + p.sw_margin_y) * p.sw_stride + (r + p.sw_margin_x) + lo;
+                    const int sws = p.sw_stride;
+                    float sw_prev[PY];
+#pragma unroll
+                    for (int ky = 0; ky < PY; ky++) sw_prev[ky] = swp[-ky * sws - 1];
+                    const int first = base_idx + lo;
+                    const unsigned char *rp = slot + smc_rec_offset(first);
+                    const int d0 = (first & 1) ? SMC_LINE_BYTES - SMC_REC_BYTES : SMC_REC_BYTES;
+                    SmcRec cur = lds_rec(rp);
+                    int j = lo;
+                    for (; j + 1 <= hi; j += 2) {
+                        const SmcRec nxt = lds_rec(rp + d0);
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][0], cur, sw_cur, acc[ky][0]);       // dx = j
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);  // dx = j - 1
+                            sw_prev[ky] = sw_cur;
+                        }
+                        rp += SMC_LINE_BYTES;
+                        cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws + 1];
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][0], nxt, sw_cur, acc[ky][0]);       // dx = j + 1
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][1], nxt, sw_prev[ky], acc[ky][1]);  // dx = j
+                            sw_prev[ky] = sw_cur;
+                        }
+                        swp += 2;
+                    }
+                    if (j <= hi) {
+#pragma unroll
+                        for (int ky = 0; ky < PY; ky++) {
+                            const float sw_cur = swp[-ky * sws];
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][0], cur, sw_cur, acc[ky][0]);
+                            pair_eval_c<C, NG, MODE, COUNT, FILM>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);
+                        }
+                    }
+                }
+            }
+}
+
+template <int C, int NG, int PY, int MODE, bool COUNT>
 __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcFilterParams p, const WarpGeom g) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [rings: nwarps x 2 x slot_bytes][sw table][rowrange][barriers: nwarps x 2]
@@ -436,7 +513,8 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
         const int xf = ti.x0 + 2 * lane;  // first of this thread's two columns
         const int base_idx = xf + p.padX - seg_start_of(p, ti.x0);  // slot index of the record at dx = 0, column kx = 0
 
-        SmcCentre<3, NG> cen[PY][2];
+        const bool film_out = p.denoise_film && ti.z == 0;  // warp-uniform
+        SmcCentre<C, NG> cen[PY][2];
         Acc acc[PY][2];
 #pragma unroll
         for (int ky = 0; ky < PY; ky++)
@@ -444,8 +522,8 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
             for (int kx = 0; kx < 2; kx++) {
                 const int yc = min(ti.y0 + ky, p.H - 1), xc = min(xf + kx, p.W - 1);
                 const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, xc + p.padX);
-                smc_make_centre<3, NG, MODE>(rc, cen[ky][kx]);
-                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = 0.f;
+                smc_make_centre<C, NG, MODE>(rc, cen[ky][kx]);
+                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = acc[ky][kx].ns = 0.f;
                 acc[ky][kx].cnt = 0;
             }
 
@@ -465,56 +543,10 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
                     "r"(parity)
                     : "memory");
             }
-            {
-                // table row of centre row ky: dy = i - r - ky  ->  row index i - ky + margin_y
-                int lo = 1 << 20, hi = -(1 << 20);
-#pragma unroll
-                for (int ky = 0; ky < PY; ky++) {
-                    const int2 rr = rowrange[i - ky + p.sw_margin_y];
-                    lo = min(lo, rr.x);
-                    hi = max(hi, rr.y);
-                }
-                if (lo <= hi) {
-                    const float *swp = sw + (i + p.sw_margin_y) * p.sw_stride + (r + p.sw_margin_x) + lo;
-                    const int sws = p.sw_stride;
-                    float sw_prev[PY];
-#pragma unroll
-                    for (int ky = 0; ky < PY; ky++) sw_prev[ky] = swp[-ky * sws - 1];
-                    const int first = base_idx + lo;
-                    const unsigned char *rp = ring + (size_t)s * g.slot_bytes + smc_rec_offset(first);
-                    const int d0 = (first & 1) ? SMC_LINE_BYTES - SMC_REC_BYTES : SMC_REC_BYTES;
-                    SmcRec cur = lds_rec(rp);
-                    int j = lo;
-                    for (; j + 1 <= hi; j += 2) {
-                        const SmcRec nxt = lds_rec(rp + d0);
-#pragma unroll
-                        for (int ky = 0; ky < PY; ky++) {
-                            const float sw_cur = swp[-ky * sws];
-                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);       // dx = j
-                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);  // dx = j - 1
-                            sw_prev[ky] = sw_cur;
-                        }
-                        rp += SMC_LINE_BYTES;
-                        cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
-#pragma unroll
-                        for (int ky = 0; ky < PY; ky++) {
-                            const float sw_cur = swp[-ky * sws + 1];
-                            pair_eval<NG, MODE, COUNT>(cen[ky][0], nxt, sw_cur, acc[ky][0]);       // dx = j + 1
-                            pair_eval<NG, MODE, COUNT>(cen[ky][1], nxt, sw_prev[ky], acc[ky][1]);  // dx = j
-                            sw_prev[ky] = sw_cur;
-                        }
-                        swp += 2;
-                    }
-                    if (j <= hi) {
-#pragma unroll
-                        for (int ky = 0; ky < PY; ky++) {
-                            const float sw_cur = swp[-ky * sws];
-                            pair_eval<NG, MODE, COUNT>(cen[ky][0], cur, sw_cur, acc[ky][0]);
-                            pair_eval<NG, MODE, COUNT>(cen[ky][1], cur, sw_prev[ky], acc[ky][1]);
-                        }
-                    }
-                }
-            }
+            if (C == 1 && !film_out)
+                warp_row<C, NG, PY, MODE, COUNT, false>(p, cen, acc, rowrange, sw, ring + (size_t)s * g.slot_bytes, i, base_idx);
+            else
+                warp_row<C, NG, PY, MODE, COUNT, true>(p, cen, acc, rowrange, sw, ring + (size_t)s * g.slot_bytes, i, base_idx);
             __syncwarp();  // every lane has read the slot
             if (i == g.nr - 2) {  // the next tile's first row goes into this slot
                 t_next = __shfl_sync(0xffffffffu, nxt_raw, 0);
@@ -532,8 +564,8 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
             }
         }
 
-        // write the tile (stat_denoiser.cu:341-344); centre fix-up as in the CTA-wide kernel
-        const SmcPtrStepSz o = (p.denoise_film && ti.z == 0) ? p.film_filtered : p.out_ptrs[ti.z];
+        // write the tile (stat_denoiser.cu:341-344 RGB, :263-273 scalar); centre fix-up as in the CTA-wide kernel
+        const SmcPtrStepSz o = (C == 3 && film_out) ? p.film_filtered : p.out_ptrs[ti.z];
 #pragma unroll
         for (int ky = 0; ky < PY; ky++) {
             const int y = ti.y0 + ky;
@@ -544,17 +576,28 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
                 if (x >= p.W) continue;
                 Acc a = acc[ky][kx];
                 const SmcRec rc = ldg_rec(img + (size_t)(y + r) * row_bytes, x + p.padX);
-                if (!smc_member<3, NG, MODE>(cen[ky][kx], rc)) {
+                if (!smc_member<C, NG, MODE>(cen[ky][kx], rc)) {
                     a.n0 = __fadd_rn(a.n0, rc.c2.x);
                     a.n1 = __fadd_rn(a.n1, rc.c2.y);
                     a.n2 = __fadd_rn(a.n2, rc.c1.z);
+                    a.ns = __fadd_rn(a.ns, rc.c1.x);
                     a.den = __fadd_rn(a.den, 1.f);
                     a.cnt += 1;
                 }
-                float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
-                op[0] = __fdiv_rn(a.n0, a.den);
-                op[1] = __fdiv_rn(a.n1, a.den);
-                op[2] = __fdiv_rn(a.n2, a.den);
+                if (C == 3) {
+                    float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
+                    op[0] = __fdiv_rn(a.n0, a.den);
+                    op[1] = __fdiv_rn(a.n1, a.den);
+                    op[2] = __fdiv_rn(a.n2, a.den);
+                } else {
+                    ((float *)(o.data + (size_t)y * o.step))[x] = __fdiv_rn(a.ns, a.den);
+                    if (film_out) {
+                        float *op = (float *)(p.film_filtered.data + (size_t)y * p.film_filtered.step) + x * 3;
+                        op[0] = __fdiv_rn(a.n0, a.den);
+                        op[1] = __fdiv_rn(a.n1, a.den);
+                        op[2] = __fdiv_rn(a.n2, a.den);
+                    }
+                }
                 if (COUNT && p.accepted && p.accepted[ti.z].data)
                     ((int *)(p.accepted[ti.z].data + (size_t)y * p.accepted[ti.z].step))[x] = a.cnt;
             }
@@ -577,8 +620,12 @@ int launch_wk(smc_context *ctx, K k, const SmcFilterParams &p, const WarpGeom &g
 
 template <int NG, int MODE>
 int launch_w(smc_context *ctx, const SmcFilterParams &p, const WarpGeom &g, size_t smem) {
-    if (p.accepted != nullptr) return launch_wk(ctx, filter_warp_kernel<NG, 2, MODE, true>, p, g, smem);
-    return launch_wk(ctx, filter_warp_kernel<NG, 2, MODE, false>, p, g, smem);
+    if (p.C == 1) {
+        if (p.accepted != nullptr) return launch_wk(ctx, filter_warp_kernel<1, NG, 2, MODE, true>, p, g, smem);
+        return launch_wk(ctx, filter_warp_kernel<1, NG, 2, MODE, false>, p, g, smem);
+    }
+    if (p.accepted != nullptr) return launch_wk(ctx, filter_warp_kernel<3, NG, 2, MODE, true>, p, g, smem);
+    return launch_wk(ctx, filter_warp_kernel<3, NG, 2, MODE, false>, p, g, smem);
 }
 
 template <typename K>
@@ -675,7 +722,7 @@ static bool warp_geometry(const SmcFilterParams &p, int PY, WarpGeom &g, size_t 
 
 // which streaming variant: per-warp rings (default when they fit) or the CTA-wide ring; SMC_STREAM_KERNEL=cta|warp
 static bool use_warp_variant(const SmcFilterParams &p, int py) {
-    if (py != 2) return false;
+    if (py != 2 && p.C == 3) return false;  // scalar statistics always take the per-warp 2 x 2 kernel
     if (const char *e = getenv("SMC_STREAM_KERNEL")) {
         if (!strcmp(e, "cta")) return false;
     }
@@ -686,7 +733,7 @@ static bool use_warp_variant(const SmcFilterParams &p, int py) {
 
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name) {
     (void)sm_count;
-    if (p.C != 3) return false;
+    if (p.C != 3 && p.C != 1) return false;
     if (p.radius < 1 || p.radius > 64) return false;
     if (p.sw_margin_y < 3 || p.sw_margin_x < 2) return false;
     if (!(p.NG == 0 || p.NG == 3 || p.NG == 6 || p.NG == 7)) return false;
@@ -694,6 +741,8 @@ bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const c
     StreamGeom g;
     size_t smem = 0;
     if (!stream_geometry(p, 2, g, smem) || !stream_geometry(p, 4, g, smem)) return false;
+    // scalar statistics (multichannelstats = false, MIS win rates): per-warp kernel only
+    if (p.C == 1 && !use_warp_variant(p, 2)) return false;
     if (name) *name = "stream";
     return true;
 }
@@ -729,7 +778,7 @@ static int stream_dispatch(smc_context *ctx, const SmcFilterParams &p, const int
         warp_geometry(p, 2, wg, wsmem);
         wg.rowrange = d_rowrange;
         static thread_local char wnm[64];
-        snprintf(wnm, sizeof(wnm), "stream-warp<NG=%d,PY=2,%s,W=%d>", p.NG, p.mode ? "moon" : "welch", wg.nwarps);
+        snprintf(wnm, sizeof(wnm), "stream-warp<%sNG=%d,PY=2,%s,W=%d>", p.C == 1 ? "C=1," : "", p.NG, p.mode ? "moon" : "welch", wg.nwarps);
         if (name) *name = wnm;
         switch (p.NG) {
             case 0: return p.mode == 0 ? launch_w<0, 0>(ctx, p, wg, wsmem) : launch_w<0, 1>(ctx, p, wg, wsmem);
@@ -740,6 +789,7 @@ static int stream_dispatch(smc_context *ctx, const SmcFilterParams &p, const int
         }
         SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: NG=%d not instantiated", p.NG);
     }
+    if (p.C != 3) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: scalar statistics need the per-warp variant");
     StreamGeom g;
     size_t smem = 0;
     if (!stream_geometry(p, py, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming filter: geometry not supported");

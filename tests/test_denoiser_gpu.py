@@ -129,23 +129,68 @@ def test_scalar_statistics_and_dual_output(ctx):
     film_f = Buffer(ctx, H, W, 3)
     g = [Buffer.from_array(ctx, b["normal"]), Buffer.from_array(ctx, b["albedo"])]
     f = [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2]
-    dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2,
-                  n=[planes["a"]["n"], planes["b"]["n"]], mean=[planes["a"]["mean"], planes["b"]["mean"]],
-                  m2=[planes["a"]["m2"], planes["b"]["m2"]], m3=[planes["a"]["m3"], planes["b"]["m3"]],
-                  film_ptrs=[planes["a"]["val"], planes["b"]["val"]], film=film, gbufs=g, gbuf_dr_factors=f,
-                  film_filtered_ptrs=[planes["a"]["out"], planes["b"]["out"]], film_filtered=film_f,
-                  denoise_film=True)
-    dn.run()
-    ctx.synchronize()
-    for tag, src in (("a", b), ("b", b2)):
+    acc = [Buffer(ctx, H, W, 1, np.int32), Buffer(ctx, H, W, 1, np.int32)]
+    got = {}
+    for kernel in (1, 2):  # generic, then the per-warp streaming kernel's scalar instantiation: same bits
+        for tag in ("a", "b"):
+            planes[tag]["out"].zero()
+        film_f.zero()
+        dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2,
+                      n=[planes["a"]["n"], planes["b"]["n"]], mean=[planes["a"]["mean"], planes["b"]["mean"]],
+                      m2=[planes["a"]["m2"], planes["b"]["m2"]], m3=[planes["a"]["m3"], planes["b"]["m3"]],
+                      film_ptrs=[planes["a"]["val"], planes["b"]["val"]], film=film, gbufs=g, gbuf_dr_factors=f,
+                      film_filtered_ptrs=[planes["a"]["out"], planes["b"]["out"]], film_filtered=film_f,
+                      denoise_film=True, accepted=acc, kernel=kernel)
+        dn.run()
+        ctx.synchronize()
+        assert dn.kernel_name.startswith("generic<C=1" if kernel == 1 else "stream-warp<C=1"), dn.kernel_name
+        got[kernel] = [planes["a"]["out"].download(), planes["b"]["out"].download(), film_f.download(),
+                       acc[0].download(), acc[1].download()]
+        dn.close()
+    for x, y in zip(got[1], got[2]):
+        assert bits_equal(x, y)
+    for k, (tag, src) in enumerate((("a", b), ("b", b2))):
         mc, dc = po.prepass(src["n"], lum(src["mean"]), lum(src["m2"]), lum(src["m3"]))
-        ref = po.filter(lum(src["film"]), [b["normal"], b["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
-                        precision="f64")
-        assert rel_mad(planes[tag]["out"].download(), ref) <= TOL
+        ref, cnt = po.filter(lum(src["film"]), [b["normal"], b["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
+                             precision="f64", want_accepted=True)
+        assert rel_mad(got[2][k], ref) <= TOL
+        assert np.array_equal(got[2][3 + k], cnt)
         if tag == "a":
             ref3 = po.filter(b["film"], [b["normal"], b["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
                              precision="f64")
-            assert rel_mad(film_f.download(), ref3) <= TOL
+            assert rel_mad(got[2][2], ref3) <= TOL
+
+
+@pytest.mark.parametrize("W,H,r,names,membership", [(333, 47, 20, ("normal", "albedo"), 0), (130, 40, 9, ("normal",), 1),
+                                                    (64, 9, 3, (), 0)])
+def test_scalar_stream_matches_generic(ctx, W, H, r, names, membership):
+    # multichannelstats = false: luminance statistics gate the filter; every streaming instantiation against the generic kernel
+    b = synth.moment_buffers(W, H, n=20, config_id=57, vary_n=True)
+    lum = lambda a: np.ascontiguousarray(a[..., 2])
+    dev = {k: Buffer.from_array(ctx, lum(b[k])) for k in ("mean", "m2", "m3")}
+    n, val, film = Buffer.from_array(ctx, b["n"]), Buffer.from_array(ctx, lum(b["film"])), Buffer.from_array(ctx, b["film"])
+    g = [Buffer.from_array(ctx, b[k]) for k in names]
+    f = [-0.5 / {"normal": 0.1, "albedo": 0.02}[k] ** 2 for k in names]
+    res = {}
+    for denoise_film in (True, False):
+        for kernel in (1, 2):
+            out, film_f = Buffer(ctx, H, W, 1), Buffer(ctx, H, W, 3)
+            dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=-0.5 / (r / 2.0) ** 2, n=[n], mean=[dev["mean"]],
+                          m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[val], film=film if denoise_film else None, gbufs=g,
+                          gbuf_dr_factors=f, film_filtered_ptrs=[out], film_filtered=film_f if denoise_film else None,
+                          denoise_film=denoise_film, membership=membership, kernel=kernel)
+            dn.run()
+            ctx.synchronize()
+            assert ("stream-warp<C=1" in dn.kernel_name) == (kernel == 2), dn.kernel_name
+            res[kernel] = (out.download(), film_f.download())
+            dn.close()
+        assert bits_equal(res[1][0], res[2][0])
+        if denoise_film:
+            assert bits_equal(res[1][1], res[2][1])
+    if membership == 0:
+        mc, dc = po.prepass(b["n"], lum(b["mean"]), lum(b["m2"]), lum(b["m3"]))
+        ref = po.filter(lum(b["film"]), [b[k] for k in names], f, r, -0.5 / (r / 2.0) ** 2, mean_corr=mc, disc=dc, precision="f64")
+        assert rel_mad(res[2][0], ref) <= TOL
 
 
 def test_multi_image_rgb_routing(ctx):
