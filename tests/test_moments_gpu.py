@@ -150,3 +150,44 @@ def test_streamed_sample_path_bit_exact(ctx, W, H, C, S):
         assert np.array_equal(got["n"], o["n"].astype(np.int32))
         for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
             assert bits_equal_nan(got[k], sq(o[k])), (k, transform)
+
+
+def _upload_state(st, o):
+    st.n.upload(o["n"].astype(np.int32))
+    for k, b in (("mean", st.mean), ("m2", st.m2), ("m3", st.m3)):
+        b.upload(o[k])
+    if st.transform:
+        st.film_mean.upload(o["film_mean"])
+        st.film_m2.upload(o["film_m2"])
+
+
+@pytest.mark.parametrize("transform", [True, False])
+def test_streamed_path_constant_pixels_and_large_n(ctx, transform):
+    """The packed fast path and its per-sample fallback (smc_moments.cu, accumulate_stream_kernel): pixels whose samples
+    are all identical (d == 0 exactly from the second sample on: black background, flat albedo), a prior state whose n
+    crosses 2^22 inside the batch (the shared-divisor division is only proven below that), and a prior state holding
+    non-finite means (every later sample must take the IEEE path).  All bit-exact against the CPU's IEEE arithmetic."""
+    W, H, C, S = 128, 6, 3, 12
+    rng = np.random.default_rng(77)
+    x = rng.gamma(0.5, 3.0, size=(S, H, W, C)).astype(np.float32)
+    x[:, 0] = 0.0                                  # black row
+    x[:, 1] = np.float32(0.18)                     # constant row
+    x[:, 2, ::2] = np.float32(1.0)                 # sqrt(1) - 1 == 0: x == 0 exactly, every other pixel (mixed lanes)
+    o = po.new_state(H, W, C)
+    o["n"][3] = 4194304 - 5                        # crosses 2^22 after five samples
+    o["n"][4, :40] = 4194304 + 7                   # already above
+    o["mean"][3:5] = rng.normal(0, 1, size=(2, W, C)).astype(np.float32)
+    o["m2"][3:5] = rng.gamma(2.0, 1e6, size=(2, W, C)).astype(np.float32)
+    o["film_mean"][3:5] = rng.gamma(1.0, 1.0, size=(2, W, C)).astype(np.float32)
+    o["mean"][5, 10:20] = np.float32(np.inf)       # poisoned prior state
+    o["film_mean"][5, 30:33] = np.float32(np.nan)
+    if not transform:
+        o["film_mean"], o["film_m2"] = o["mean"], o["m2"]
+    st = MomentState(ctx, W, H, C, transform=transform)
+    _upload_state(st, o)
+    st.add_samples(x)
+    po.accumulate(o, x, transform=transform, use_sqrt=True)
+    got = st.download()
+    assert np.array_equal(got["n"], o["n"].astype(np.int32))
+    for k in ("mean", "m2", "m3", "film_mean", "film_m2"):
+        assert bits_equal_nan(got[k], o[k]), (k, transform)
