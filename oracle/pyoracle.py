@@ -254,3 +254,50 @@ class RefFilter:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own CPU accumulation (oracle/_ref/libstatmc_ref_accum*.so = src/statistics/estimator.h compiled
+# unmodified around oracle/ref_accum_harness.cpp).  Runs anywhere.
+# ---------------------------------------------------------------------------------------------------------------------
+REF_ACCUM_LIB = os.path.join(_HERE, "_ref", "libstatmc_ref_accum.so")
+REF_ACCUM_LIB_FMA = os.path.join(_HERE, "_ref", "libstatmc_ref_accum_fma.so")
+
+
+def ref_accum_available(fma: bool = False) -> bool:
+    return os.path.exists(REF_ACCUM_LIB_FMA if fma else REF_ACCUM_LIB)
+
+
+def _ref_accum(fma: bool = False):
+    path = REF_ACCUM_LIB_FMA if fma else REF_ACCUM_LIB
+    if path not in _ref_libs:
+        l = C.CDLL(path)
+        l.smr_accumulate.restype = C.c_int
+        l.smr_box_cox.restype = C.c_float
+        l.smr_box_cox.argtypes = [C.c_float, C.c_float]
+        _ref_libs[path] = l
+    return _ref_libs[path]
+
+
+def ref_accumulate(state: dict, samples: np.ndarray, transform: bool = True, max_moment: int = 3, fma: bool = False):
+    """StatTile<T>::Add[Transform]SampleM{1,2,3} of the reference (estimator.h:162-232), in place on `state`
+    (same layout as accumulate()).  fma=True: the build with FMA contraction, as the reference's README compiles it."""
+    s = np.ascontiguousarray(samples, dtype=np.float32)
+    Cc = state["mean"].shape[2] if state["mean"].ndim == 3 else 1
+    assert state["n"].dtype == np.int64 and all(state[k].dtype == np.float32 for k in ("mean", "m2", "m3"))
+    f = lambda k: state[k].ctypes.data_as(C.c_void_p)
+    rc = _ref_accum(fma).smr_accumulate(C.c_int64(state["n"].size), Cc, s.shape[0], s.ctypes.data_as(C.c_void_p),
+                                        int(transform), max_moment, f("n"), f("mean"), f("m2"), f("m3"),
+                                        f("film_mean"), f("film_m2"))
+    if rc != 0:
+        raise ValueError("reference accumulation: unsupported channel count %d" % Cc)
+
+
+def ref_box_cox(v: float, lam: float = 0.5, fma: bool = False) -> float:
+    return float(_ref_accum(fma).smr_box_cox(v, lam))
+
+
+def ref_tile_pixel_layout(channels: int):
+    size, align = C.c_int(0), C.c_int(0)
+    _ref_accum().smr_tile_pixel_layout(channels, C.byref(size), C.byref(align))
+    return size.value, align.value

@@ -40,3 +40,35 @@ def bits_equal_nan(a, b):
 def small_buffers(W=96, H=64, n=32, seed=11, vary_n=False):
     from statmc_b200 import synth
     return synth.moment_buffers(W, H, n=n, config_id=seed, vary_n=vary_n)
+
+
+def accum_golden():
+    """tests/golden/ref_accum_*.npz: the reference's own StatTile accumulation (estimator.h compiled unmodified,
+    tools/make_golden_accum.py) on seeded sample batches.  -> list of (name, config, npz)."""
+    import glob
+    import json
+    import os
+    out = []
+    for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_accum_*.npz"))):
+        z = np.load(p)
+        out.append((os.path.basename(p)[:-4], json.loads(str(z["config"])), z))
+    return out
+
+
+PLANES = ("mean", "m2", "m3", "film_mean", "film_m2")
+
+
+def accum_scale(state):
+    """per-pixel scale of the k-th central moment sum, for the scale-aware relative error of the accumulation
+    parity criterion: sigma for the means, n*sigma^2 for M2, n*sigma^3 for M3 (sigma from the state's
+    own M2; floor 1e-30)."""
+    n = np.maximum(state["n"].astype(np.float64), 2).reshape(state["n"].shape + (1,))
+    m2 = state["m2"].astype(np.float64).reshape(n.shape[:2] + (-1,))
+    fm2 = state["film_m2"].astype(np.float64).reshape(n.shape[:2] + (-1,))
+    sigma = np.sqrt(np.maximum(m2, 1e-30) / n)
+    fsigma = np.sqrt(np.maximum(fm2, 1e-30) / n)
+    # states whose M2 is not tracked (M1 configurations) fall back to |mean|
+    mean = np.abs(state["mean"].astype(np.float64)).reshape(m2.shape)
+    sigma = np.where(m2 > 0, sigma, np.maximum(mean, 1e-30))
+    fsigma = np.where(fm2 > 0, fsigma, np.maximum(mean, 1e-30))
+    return {"mean": sigma, "m2": n * sigma ** 2, "m3": n * sigma ** 3, "film_mean": fsigma, "film_m2": n * fsigma ** 2}
