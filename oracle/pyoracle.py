@@ -301,3 +301,80 @@ def ref_tile_pixel_layout(channels: int):
     size, align = C.c_int(0), C.c_int(0)
     _ref_accum().smr_tile_pixel_layout(channels, C.byref(size), C.byref(align))
     return size.value, align.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own HOST code of the path (src/statistics/estimator.cpp + buffer.cpp, compiled unmodified) running on
+# libstatmc_b200.so through integration/opencv_link_shim.cpp (oracle/_ref/libstatmc_ref_estimator.so, built by
+# oracle/Makefile around oracle/ref_estimator_harness.cpp).  The denoise entry needs a GPU; the shim checks do not.
+# ---------------------------------------------------------------------------------------------------------------------
+REF_ESTIMATOR_LIB = os.path.join(_HERE, "_ref", "libstatmc_ref_estimator.so")
+
+
+def ref_estimator_available() -> bool:
+    return os.path.exists(REF_ESTIMATOR_LIB)
+
+
+def _ref_estimator():
+    if REF_ESTIMATOR_LIB not in _ref_libs:
+        l = C.CDLL(REF_ESTIMATOR_LIB)
+        l.smr_estimator_last_error.restype = C.c_char_p
+        _ref_libs[REF_ESTIMATOR_LIB] = l
+    return _ref_libs[REF_ESTIMATOR_LIB]
+
+
+def ref_estimator_denoise(bufs: dict, radius: int, sd: float, normal_sd: float = 0.1, albedo_sd: float = 0.02,
+                          denoise_film: bool = True, acrr: bool = False, dump_stem: str | None = None,
+                          dump_regex: str = "film.*", dump_suffix: str = "", reps: int = 1) -> dict:
+    """pbrt::Estimator (the reference's, unmodified): AllocateBuffers, planes filled, Upload / Denoise / Download /
+    Synchronize (statpath.cpp:406-418).  bufs: n [nb,]H,W int32; mean, m2, m3, film_mean [nb,]H,W[,3]; film, normal,
+    albedo H,W,3.  -> film_f, film_mean_f, mean_corr, disc, cuda_time_ns, n_registered."""
+    l = _ref_estimator()
+    film = np.ascontiguousarray(bufs["film"], np.float32)
+    H, W = film.shape[:2]
+    n = np.ascontiguousarray(bufs["n"], np.int32)
+    nb = 1 if n.ndim == 2 else n.shape[0]
+    Cc = 3 if np.asarray(bufs["mean"]).shape[-1] == 3 and np.asarray(bufs["mean"]).ndim == n.ndim + 1 else 1
+    shp = (nb, H, W, Cc)
+    g = lambda k: np.ascontiguousarray(bufs[k], np.float32).reshape(shp)
+    mean, m2, m3 = g("mean"), g("m2"), g("m3")
+    film_mean = g("film_mean") if "film_mean" in bufs else (film.reshape(shp) if Cc == 3 and nb == 1 else mean)
+    normal, albedo = (np.ascontiguousarray(bufs[k], np.float32) for k in ("normal", "albedo"))
+    out = {"film_f": np.zeros((H, W, 3), np.float32), "film_mean_f": np.zeros(shp, np.float32),
+           "mean_corr": np.zeros(shp, np.float32), "disc": np.zeros(shp, np.float32)}
+    ns, nreg = C.c_double(0), C.c_int(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    enc = lambda s: None if s is None else s.encode()
+    rc = l.smr_estimator_denoise(W, H, Cc, nb, C.c_float(sd), int(radius), int(denoise_film), int(acrr), p(n), p(mean),
+                                 p(m2), p(m3), p(film_mean), p(film), p(normal), C.c_float(normal_sd), p(albedo),
+                                 C.c_float(albedo_sd), p(out["film_f"]), p(out["film_mean_f"]), p(out["mean_corr"]),
+                                 p(out["disc"]), enc(dump_stem), enc(dump_regex), enc(dump_suffix), int(reps),
+                                 C.byref(ns), C.byref(nreg))
+    if rc != 0:
+        raise RuntimeError("reference Estimator on statmc_b200: " + (l.smr_estimator_last_error() or b"").decode())
+    if n.ndim == 2:
+        sq = (H, W, 3) if Cc == 3 else (H, W)
+        for k in ("film_mean_f", "mean_corr", "disc"):
+            out[k] = out[k].reshape(sq)
+    out["cuda_time_ns"], out["n_registered"] = ns.value, nreg.value
+    return out
+
+
+def shim_mat_semantics() -> int:
+    return int(_ref_estimator().smr_shim_mat_semantics())
+
+
+def shim_pfm_roundtrip(filename: str, data: np.ndarray, as_int32: bool = False) -> np.ndarray:
+    """buffer.cpp:40-53 (Write) then statpath.cpp:449-454 (ReadFile) through the shim's cv::imwrite / imread / cvtColor /
+    convertTo."""
+    l = _ref_estimator()
+    a = np.ascontiguousarray(data, np.float32)
+    H, W = a.shape[:2]
+    Cc = 1 if a.ndim == 2 else a.shape[2]
+    back = np.zeros(a.shape, np.int32 if as_int32 else np.float32)
+    rc = l.smr_shim_pfm_roundtrip(filename.encode(), W, H, Cc, a.ctypes.data_as(C.c_void_p),
+                                  None if as_int32 else back.ctypes.data_as(C.c_void_p),
+                                  back.ctypes.data_as(C.c_void_p) if as_int32 else None)
+    if rc != 0:
+        raise RuntimeError((l.smr_estimator_last_error() or b"").decode())
+    return back

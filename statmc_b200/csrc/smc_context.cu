@@ -173,7 +173,8 @@ extern "C" void smc_context_destroy(smc_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->cached) smc_denoiser_destroy(ctx->cached);
+    for (smc_denoiser *c : ctx->cached)
+        if (c) smc_denoiser_destroy(c);
     cudaFree(ctx->d_lut);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

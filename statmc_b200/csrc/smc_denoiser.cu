@@ -663,10 +663,11 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
         std::memcpy(k, ints, sizeof(ints)); k += sizeof(ints);
         std::memcpy(k, &ds_factor, sizeof(float));
     }
-    smc_denoiser *d = ctx->cached;
-    if (!d || key != ctx->cached_key) {
+    const int slot = channels == 3 ? 1 : 0;
+    smc_denoiser *d = ctx->cached[slot];
+    if (!d || key != ctx->cached_key[slot]) {
         if (d) smc_denoiser_destroy(d);
-        ctx->cached = nullptr;
+        ctx->cached[slot] = nullptr;
         std::vector<unsigned char> gch(std::max(n_gbufs, 1));
         std::vector<float> gf(std::max(n_gbufs, 1));
         if (n_gbufs > 0) {
@@ -702,8 +703,8 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
             return rc;
         }
         SMC_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->cached = d;
-        ctx->cached_key = key;
+        ctx->cached[slot] = d;
+        ctx->cached_key[slot] = key;
     }
     d->t_n = (const SmcPtrStepSz *)n_ptrs; d->t_mean = (const SmcPtrStepSz *)mean_ptrs;
     d->t_m2 = (const SmcPtrStepSz *)m2_ptrs; d->t_m3 = (const SmcPtrStepSz *)m3_ptrs;

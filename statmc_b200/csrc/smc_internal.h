@@ -83,8 +83,10 @@ struct smc_context {
     float h_lut[SMC_T_LUT_ENTRIES];
     float *d_lut = nullptr;  // device copy of the active table
     // scratch plan cached for smc_filter_device_tables
-    struct smc_denoiser *cached = nullptr;
-    std::vector<unsigned char> cached_key;
+    // (one slot per element type: Estimator::Denoise calls filter<float> and filter<float3> back to back when both
+    // groups are populated, estimator.cpp:434-488, and neither plan should evict the other)
+    struct smc_denoiser *cached[2] = {nullptr, nullptr};
+    std::vector<unsigned char> cached_key[2];
 };
 
 struct smc_buffer {
