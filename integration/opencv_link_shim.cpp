@@ -459,7 +459,14 @@ void GpuMat::upload(InputArray arr, Stream &) {
     if (m.rows <= 0 || m.cols <= 0 || !m.data) return;
     create(m.rows, m.cols, m.type());
     const Plane2D p = plane_of(*this);
-    check(smc_buffer_upload(p.buf, m.data, m.step.p[0]), "GpuMat::upload");
+    const size_t dev_row = ((p.row_bytes + 3) / 4) * 4;  // byte matrices live in whole words on the device (ShimAllocator)
+    if (dev_row == p.row_bytes) {
+        check(smc_buffer_upload(p.buf, m.data, m.step.p[0]), "GpuMat::upload");
+    } else {  // pad the rows on the way (pageable source: the copy is staged before the call returns)
+        std::vector<uchar> tmp(dev_row * (size_t)m.rows, 0);
+        for (int y = 0; y < m.rows; y++) std::memcpy(tmp.data() + dev_row * y, m.data + m.step.p[0] * y, p.row_bytes);
+        check(smc_buffer_upload(p.buf, tmp.data(), dev_row), "GpuMat::upload");
+    }
 }
 void GpuMat::upload(InputArray arr) {
     upload(arr, Stream::Null());
@@ -470,7 +477,15 @@ void GpuMat::download(OutputArray _dst, Stream &) const {
     if (!data) fail("GpuMat::download of an empty matrix");
     Mat &dst = out_mat(_dst, rows, cols, type());
     const Plane2D p = plane_of(*this);
-    check(smc_buffer_download(p.buf, dst.data, dst.step.p[0]), "GpuMat::download");
+    const size_t dev_row = ((p.row_bytes + 3) / 4) * 4;
+    if (dev_row == p.row_bytes) {
+        check(smc_buffer_download(p.buf, dst.data, dst.step.p[0]), "GpuMat::download");
+    } else {
+        std::vector<uchar> tmp(dev_row * (size_t)rows);
+        check(smc_buffer_download(p.buf, tmp.data(), dev_row), "GpuMat::download");
+        check(smc_synchronize(shim().ctx), "GpuMat::download");
+        for (int y = 0; y < rows; y++) std::memcpy(dst.data + dst.step.p[0] * y, tmp.data() + dev_row * y, p.row_bytes);
+    }
 }
 void GpuMat::download(OutputArray _dst) const {
     download(_dst, Stream::Null());
