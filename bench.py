@@ -37,6 +37,18 @@ NORMAL_SD, ALBEDO_SD = 0.1, 0.02
 ALGO_BYTES_PER_PX = 88          # 76 B compulsory reads + 12 B write, RGB default
 PREPASS_BYTES_PER_PX = 76 + 72  # what the prepass kernel itself moves: planes in, 64-B record (+8 B line pad) out
 FP32_LANE_OPS_PER_PAIR = 24     # FP32-pipe lane-cycles per pair evaluation of the streaming kernel (SASS count)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures committed under profiles/
+# (single GPU, default kernels, the 4K workload; other configurations report null)
+NCU_TRAFFIC = {
+    "filter": {"bytes": 615.873024e6 + 98.084864e6, "source": "profiles/r1c_ncu_filter.txt"},
+    "prepass": {"bytes": 774.772736e6 + 575.187968e6, "source": "profiles/r1c_ncu_prepass.txt"},
+    "accum": {"bytes": 1.061725e9 + 241.993216e6, "source": "profiles/r1d_ncu_accum.txt"},
+}
+
+
+def ncu_traffic(which, args, world):
+    ok = world == 1 and args.workload == "4k" and not args.radius and args.channels == 3 and args.gbufs == 2 and args.kernel == 0
+    return NCU_TRAFFIC[which]["bytes"] if ok else None
 
 
 def peaks():
@@ -349,7 +361,9 @@ def main():
         bytes_per_launch = S * srows * W * 12 + srows * W * 2 * 64
         accum = {"value": nsmp / t / 1e9, "unit": "Gsamples/s", "batch": S, "pixels_per_gpu": srows * W,
                  "roofline": {"bound": "hbm", "achieved": bytes_per_launch / t / 1e9, "peak": pk["hbm_gbs"],
-                              "unit": "GB/s", "frac": bytes_per_launch / t / 1e9 / pk["hbm_gbs"], "traffic": None}}
+                              "unit": "GB/s", "frac": bytes_per_launch / t / 1e9 / pk["hbm_gbs"],
+                              "algorithmic_bytes": bytes_per_launch, "traffic": ncu_traffic("accum", args, world),
+                              "traffic_source": NCU_TRAFFIC["accum"]["source"]}}
         del smp
 
     if rank == 0:
@@ -373,7 +387,9 @@ def main():
                        "kernel": dn.kernel_name},
             "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_PER_PX * band_px / (f_ms * 1e-3) / 1e9,
                          "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ALGO_BYTES_PER_PX * band_px / (f_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "frac": ALGO_BYTES_PER_PX * band_px / (f_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                         "algorithmic_bytes": ALGO_BYTES_PER_PX * band_px, "traffic": ncu_traffic("filter", args, world),
+                         "traffic_source": NCU_TRAFFIC["filter"]["source"],
                          "kernel": "filter (" + dn.kernel_name + ")", "kernel_ms": f_ms, "peak_source": pk["source"],
                          "note": "the filter is FP32-pipe bound (see fp32); HBM fraction given for the 88 B/px algorithmic bytes"},
             "fp32": {"bound": "fp32-pipe", "pairs_per_launch": pairs, "lane_ops_per_pair": FP32_LANE_OPS_PER_PAIR,
@@ -383,7 +399,9 @@ def main():
             "roofline_prepass": {"bound": "hbm", "achieved": PREPASS_BYTES_PER_PX * rows * W / (p_ms * 1e-3) / 1e9,
                                  "peak": pk["hbm_gbs"], "unit": "GB/s",
                                  "frac": PREPASS_BYTES_PER_PX * rows * W / (p_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                 "kernel_ms": p_ms},
+                                 "kernel_ms": p_ms, "algorithmic_bytes": PREPASS_BYTES_PER_PX * rows * W,
+                                 "traffic": ncu_traffic("prepass", args, world),
+                                 "traffic_source": NCU_TRAFFIC["prepass"]["source"]},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "accum": accum,
         }
         if world == 1 and not args.no_cpu_baseline:

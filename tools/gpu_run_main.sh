@@ -8,6 +8,7 @@ echo "nproc=$(nproc)" >> gpurun_out/gpu.txt
 echo "== smoke"; timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.txt 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.txt
 echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest.txt 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest.txt
 echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_4k_$R.json 2> gpurun_out/bench_4k.err; echo "bench rc=$?"; cat gpurun_out/bench_4k_$R.json; tail -5 gpurun_out/bench_4k.err
+for wl in 720p 1080p; do timeout 300 python bench.py --workload $wl --no-cpu-baseline --no-accum --steps 10 --warmup 3 > gpurun_out/bench_${wl}_$R.json 2>> gpurun_out/bench_4k.err; python -c "import json;d=json.loads(open('gpurun_out/bench_${wl}_$R.json').read().splitlines()[-1]);print('$wl',round(d['value'],1),'Mpix/s e2e',round(d['e2e']['value'],1))"; done
 echo "== bench ref"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_4k_$R.json 2> gpurun_out/bench_ref_4k.err; echo "rc=$?"; cat gpurun_out/bench_ref_4k_$R.json; tail -5 gpurun_out/bench_ref_4k.err
 B="python bench.py --no-cpu-baseline --no-e2e"
 echo "== ncu launch list"
