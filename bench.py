@@ -40,9 +40,9 @@ FP32_LANE_OPS_PER_PAIR = 24     # FP32-pipe lane-cycles per pair evaluation of t
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures committed under profiles/
 # (single GPU, default kernels, the 4K workload; other configurations report null)
 NCU_TRAFFIC = {
-    "filter": {"bytes": 615.873024e6 + 98.084864e6, "source": "profiles/r1c_ncu_filter.txt"},
-    "prepass": {"bytes": 774.772736e6 + 575.187968e6, "source": "profiles/r1c_ncu_prepass.txt"},
-    "accum": {"bytes": 1.061725e9 + 241.993216e6, "source": "profiles/r1d_ncu_accum.txt"},
+    "filter": {"bytes": 616.318464e6 + 95.273216e6, "source": "profiles/r1e_ncu_filter.txt"},
+    "prepass": {"bytes": 776.474368e6 + 575.209472e6, "source": "profiles/r1e_ncu_prepass.txt"},
+    "accum": {"bytes": 1.061725e9 + 242.227456e6, "source": "profiles/r1e_ncu_accum.txt"},
 }
 
 
@@ -124,6 +124,39 @@ def cpu_baseline(W, H, radius, sd, n, seconds_target=12.0):
     return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
             "sample": "oracle/statmc_oracle.c (float32, OpenMP) on a %d x %d band of the workload, r=%d: %.1f s"
                       % (W, rows2, radius, dt)}
+
+
+def cpu_accum_baseline(W, S=16, seconds_target=6.0, fma=True):
+    """Stage 1 on the host cores with the REFERENCE'S OWN code: StatTile<Vec3>::AddTransformSampleM3 (estimator.h:162-226,
+    compiled unmodified into oracle/_ref/libstatmc_ref_accum_fma.so the way the reference's README builds it, -O2 + FMA
+    contraction), threaded over row chunks like ParallelFor2D over tiles (statpath.cpp:132,218), one chunk per core.
+    A bounded sample: S samples on 32 rows per core, repeated until ~seconds_target.  Reported as baseline only."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    if not po.ref_accum_available(fma=fma):
+        return None
+    cores = os.cpu_count() or 1
+    rows = 32
+    rng = np.random.default_rng(7)
+    chunks = []
+    for _ in range(cores):
+        st = po.new_state(rows, W)
+        smp = rng.uniform(0.01, 4.0, size=(S, rows, W, 3)).astype(np.float32)
+        chunks.append((st, smp))
+    run = lambda c: po.ref_accumulate(c[0], c[1], transform=True, max_moment=3, fma=fma)  # ctypes releases the GIL
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(run, chunks))  # warm-up (page faults, library load)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            list(ex.map(run, chunks))
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt >= seconds_target or reps >= 200:
+                break
+    nsmp = reps * cores * S * rows * W
+    return {"value": nsmp / dt / 1e9, "unit": "Gsamples/s", "cores": cores, "kind": "reference",
+            "sample": "StatTile<Vec3>::AddTransformSampleM3 (estimator.h compiled unmodified, -O2 -march=x86-64-v3 FMA) on "
+                      "%d chunks of %d x %d px, %d samples/px, %d passes: %.1f s" % (cores, W, rows, S, reps, dt)}
 
 
 def main():
@@ -406,6 +439,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(W, H, radius, sd, n)
+            if accum is not None:
+                accum["cpu_baseline"] = cpu_accum_baseline(W)
         print(json.dumps(res), flush=True)
     dn.close()
     if world > 1:
@@ -490,6 +525,7 @@ def reference_arm(args, local):
                  "cpu_baseline": {"value": None, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "reference",
                                   "sample": "the reference's denoiser has no CPU implementation; this arm runs its own CUDA "
                                             "kernels (stat_denoiser.cu, unmodified, sm_100a) on one B200"}})
+    base["accum"] = cpu_accum_baseline(W)  # stage 1 does have a CPU implementation in the reference: time it too
     print(json.dumps(base), flush=True)
     return 0
 
