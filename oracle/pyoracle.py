@@ -325,10 +325,11 @@ def _ref_estimator():
 
 def ref_estimator_denoise(bufs: dict, radius: int, sd: float, normal_sd: float = 0.1, albedo_sd: float = 0.02,
                           denoise_film: bool = True, acrr: bool = False, dump_stem: str | None = None,
-                          dump_regex: str = "film.*", dump_suffix: str = "", reps: int = 1) -> dict:
+                          dump_regex: str = "film.*", dump_suffix: str = "", reps: int = 1, mis: dict | None = None) -> dict:
     """pbrt::Estimator (the reference's, unmodified): AllocateBuffers, planes filled, Upload / Denoise / Download /
     Synchronize (statpath.cpp:406-418).  bufs: n [nb,]H,W int32; mean, m2, m3, film_mean [nb,]H,W[,3]; film, normal,
-    albedo H,W,3.  -> film_f, film_mean_f, mean_corr, disc, cuda_time_ns, n_registered."""
+    albedo H,W,3.  mis (statistical MIS, optional): n [2,nbm,H,W] int32, mean / m2 / m3 [2,nbm,H,W] float32 (BSDF and light
+    win rates per tracked bounce).  -> film_f, film_mean_f, mean_corr, disc, cuda_time_ns, n_registered[, mis_f]."""
     l = _ref_estimator()
     film = np.ascontiguousarray(bufs["film"], np.float32)
     H, W = film.shape[:2]
@@ -343,13 +344,20 @@ def ref_estimator_denoise(bufs: dict, radius: int, sd: float, normal_sd: float =
     out = {"film_f": np.zeros((H, W, 3), np.float32), "film_mean_f": np.zeros(shp, np.float32),
            "mean_corr": np.zeros(shp, np.float32), "disc": np.zeros(shp, np.float32)}
     ns, nreg = C.c_double(0), C.c_int(0)
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    nbm, mn, mm, mm2, mm3 = 0, None, None, None, None
+    if mis is not None:
+        mn = np.ascontiguousarray(mis["n"], np.int32)
+        nbm = mn.shape[1]
+        mm, mm2, mm3 = (np.ascontiguousarray(mis[k], np.float32) for k in ("mean", "m2", "m3"))
+        assert mn.shape == (2, nbm, H, W) and mm.shape == mn.shape
+        out["mis_f"] = np.zeros(mn.shape, np.float32)
     enc = lambda s: None if s is None else s.encode()
     rc = l.smr_estimator_denoise(W, H, Cc, nb, C.c_float(sd), int(radius), int(denoise_film), int(acrr), p(n), p(mean),
                                  p(m2), p(m3), p(film_mean), p(film), p(normal), C.c_float(normal_sd), p(albedo),
                                  C.c_float(albedo_sd), p(out["film_f"]), p(out["film_mean_f"]), p(out["mean_corr"]),
                                  p(out["disc"]), enc(dump_stem), enc(dump_regex), enc(dump_suffix), int(reps),
-                                 C.byref(ns), C.byref(nreg))
+                                 C.byref(ns), C.byref(nreg), nbm, p(mn), p(mm), p(mm2), p(mm3), p(out.get("mis_f")))
     if rc != 0:
         raise RuntimeError("reference Estimator on statmc_b200: " + (l.smr_estimator_last_error() or b"").decode())
     if n.ndim == 2:

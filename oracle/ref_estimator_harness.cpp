@@ -53,13 +53,18 @@ extern "C" const char *smr_estimator_last_error() { return g_err.c_str(); }
  *   film_f   [H][W][3] out ("film-f"); film_mean_f [nb][H][W][C] out ("t0-b<j>-film-mean-f"); mean_corr, disc: [nb][H][W][C] out
  *   dump_stem  if non-NULL, OutputBufferSelection(reg, regex(dump_regex), dump_stem + ".pfm").Write(dump_suffix)
  *   reps       how many times the Upload/Denoise/Download/Synchronize section runs; *cuda_time_ns = the last one's time
+ *   nbm > 0    statistical MIS (enableSMIS, statpath.cpp:1056-1080): BSDF and light win-rate statistics, scalar, untransformed,
+ *              nbm tracked bounces each: mis_n [2][nbm][H][W] int32, mis_mean / mis_m2 / mis_m3 [2][nbm][H][W];
+ *              mis_f [2][nbm][H][W] out ("t1-b<j>-film-mean-f", "t2-b<j>-film-mean-f").  With C = 3 this populates BOTH CUDA
+ *              groups, so Estimator::Denoise launches filter<float> and then filter<float3> (estimator.cpp:434-488).
  */
 extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD, int radius, int denoiseFilm, int acrr,
                                      const int32_t *n, const float *mean, const float *m2, const float *m3,
                                      const float *film_mean, const float *film, const float *normal, float normalSD,
                                      const float *albedo, float albedoSD, float *film_f, float *film_mean_f, float *mean_corr,
                                      float *disc, const char *dump_stem, const char *dump_regex, const char *dump_suffix,
-                                     int reps, double *cuda_time_ns, int *n_registered) {
+                                     int reps, double *cuda_time_ns, int *n_registered, int nbm, const int32_t *mis_n,
+                                     const float *mis_mean, const float *mis_m2, const float *mis_m3, float *mis_f) {
     using namespace pbrt;
     try {
         if ((C != 1 && C != 3) || nb < 1 || W < 1 || H < 1) throw std::runtime_error("bad shape");
@@ -76,6 +81,19 @@ extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD
             cfg.nBounces = cfg.bounceEnd - cfg.bounceStart;
             cfg.nChannels = (unsigned char)C;
             cfg.transform = true;
+            cfg.maxMoment = 3;
+            cfg.cudaGroups.push_back(DenoiseGroup);
+        }
+        for (int t = 0; t < (nbm > 0 ? 2 : 0); t++) {
+            auto &cfg = cfgs[t == 0 ? MISBSDFWinRate : MISLightWinRate];
+            cfg.type = t == 0 ? MISBSDFWinRate : MISLightWinRate;
+            cfg.index = cfgs.nEnabled++;
+            cfg.enable = true;
+            cfg.bounceStart = 0;
+            cfg.bounceEnd = (unsigned char)nbm;
+            cfg.nBounces = (unsigned char)nbm;
+            cfg.nChannels = 1;
+            cfg.transform = false;
             cfg.maxMoment = 3;
             cfg.cudaGroups.push_back(DenoiseGroup);
         }
@@ -100,7 +118,8 @@ extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD
         //      estimator, AllocateBuffers ---------------------------------------------------------------------------------
         Buffer filmBuffer("film", Mat3(H, W));
         BufferRegistry reg(filmBuffer);
-        Estimator est(filmBuffer, cfgs, filterSD, (unsigned char)radius, denoiseFilm != 0, acrr != 0, false, 1, reg,
+        const int iNormal = cfgs[StatNormal].index, iAlbedo = cfgs[StatAlbedo].index;
+        Estimator est(filmBuffer, cfgs, filterSD, (unsigned char)radius, denoiseFilm != 0, acrr != 0, nbm > 0, 1, reg,
                       Bounds2i(Point2i(0, 0), Point2i(W, H)), nullptr);
         est.AllocateBuffers(reg);
         if (n_registered) *n_registered = (int)reg.buffers.size();
@@ -116,8 +135,16 @@ extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD
             put(est.m3Buffers[0][j], m3 + j * px * C, px * C * 4);
             put(est.filmBuffers[0][j], film_mean + j * px * C, px * C * 4);
         }
-        put(est.filmBuffers[1][0], normal, px * 12);  // features: mean == film-mean (no transform, estimator.cpp:128-136)
-        put(est.filmBuffers[2][0], albedo, px * 12);
+        put(est.filmBuffers[iNormal][0], normal, px * 12);  // features: mean == film-mean (no transform, estimator.cpp:128-136)
+        put(est.filmBuffers[iAlbedo][0], albedo, px * 12);
+        for (int t = 0; t < (nbm > 0 ? 2 : 0); t++)
+            for (int j = 0; j < nbm; j++) {
+                const size_t o = ((size_t)t * nbm + j) * px;
+                put(est.nBuffers[1 + t][j], mis_n + o, px * 4);
+                put(est.meanBuffers[1 + t][j], mis_mean + o, px * 4);  // == film-mean (untransformed type)
+                put(est.m2Buffers[1 + t][j], mis_m2 + o, px * 4);
+                put(est.m3Buffers[1 + t][j], mis_m3 + o, px * 4);
+            }
 
         // ---- statpath.cpp:406-418 ------------------------------------------------------------------------------------
         double ns = 0;
@@ -135,7 +162,7 @@ extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD
         for (int j = 0; j < nb; j++) {
             est.meanCorrBuffers[0][j].download(est.stream);
             est.discriminatorBuffers[0][j].download(est.stream);
-            if (C == 1 && !acrr) est.filmFilteredBuffers[0][j].download(est.stream);  // only ACRR/SMIS download them (estimator.cpp:236-240)
+            if (C == 1 && !acrr && nbm == 0) est.filmFilteredBuffers[0][j].download(est.stream);  // only ACRR/SMIS download them (estimator.cpp:236-240)
         }
         est.Synchronize();
 
@@ -145,6 +172,10 @@ extern "C" int smr_estimator_denoise(int W, int H, int C, int nb, float filterSD
             if (mean_corr) get(est.meanCorrBuffers[0][j].mat, mean_corr + j * px * C, px * C * 4);
             if (disc) get(est.discriminatorBuffers[0][j].mat, disc + j * px * C, px * C * 4);
         }
+
+        for (int t = 0; t < (nbm > 0 ? 2 : 0); t++)
+            for (int j = 0; j < nbm; j++)
+                if (mis_f) get(est.filmFilteredBuffers[1 + t][j].mat, mis_f + ((size_t)t * nbm + j) * px, px * 4);
 
         if (dump_stem) {
             OutputBufferSelection sel(reg, std::regex(dump_regex ? dump_regex : "film.*"), std::string(dump_stem) + ".pfm");

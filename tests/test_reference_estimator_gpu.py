@@ -60,6 +60,35 @@ def test_reference_estimator_scalar_acrr_bounces(ctx):
             assert rel_mad(got["film_f"], ref_film) <= 1e-4
 
 
+def test_reference_estimator_smis_both_cuda_groups(ctx):
+    # multichannelstats + denoiseimage + smis, 2 tracked bounces: RGB radiance (t0) in the float3 group, BSDF / light win
+    # rates (t1, t2; scalar, untransformed) in the float group.  Estimator::Denoise launches filter<float> first -- its
+    # image 0 (t1-b0) filters `film` into `film-f` with the win-rate gate -- and filter<float3> then overwrites film-f with
+    # the radiance-gated result (estimator.cpp:434-488).  Both plans stay cached side by side.
+    W, H, r, sd, spp, nbm = 110, 52, 6, 3.0, 32, 2
+    b = synth.moment_buffers(W, H, n=spp, config_id=86)
+    mis = {k: [] for k in ("n", "mean", "m2", "m3")}
+    for t in (0, 1):
+        for j in range(nbm):
+            s = synth.moment_buffers(W, H, n=spp, config_id=87 + 2 * t + j)
+            mis["n"].append(s["n"])
+            for k in ("mean", "m2", "m3"):
+                mis[k].append(np.ascontiguousarray(s[k][..., (t + j) % 3]))
+    mis = {k: np.stack(v).reshape(2, nbm, H, W) for k, v in mis.items()}
+    for rep in range(2):  # second call: both cached plans are reused
+        got = po.ref_estimator_denoise(b, r, sd, mis=mis)
+        assert got["n_registered"] == 2 + 10 * (1 + 2 * nbm + 2)
+        ora = po.denoise(b, radius=r, sd=sd, precision="f64", want_aux=True)
+        assert bits_equal(got["mean_corr"], ora["mean_corr"]) and bits_equal(got["disc"], ora["disc"])
+        assert rel_mad(got["film_f"], ora["film_f"]) <= 1e-4  # the RGB launch has the last word on film-f
+        gb, fac, dsf = [b["normal"], b["albedo"]], [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2], -0.5 / (sd * sd)
+        for t in (0, 1):
+            for j in range(nbm):
+                mc, dc = po.prepass(mis["n"][t, j], mis["mean"][t, j], mis["m2"][t, j], mis["m3"][t, j])
+                ref = po.filter(mis["mean"][t, j], gb, fac, r, dsf, mean_corr=mc, disc=dc, precision="f64")
+                assert rel_mad(got["mis_f"][t, j], ref) <= 1e-4, (rep, t, j)
+
+
 def test_reference_dump_feeds_our_replay(ctx, tmp_path):
     # the reference's OutputBufferSelection::Write (buffer.cpp:40-53) dumps every registered plane as PFM through the shim;
     # build/smc_denoise (our `pbrt --denoise` replay) reads that dump back and must reproduce film-f bit for bit
