@@ -23,6 +23,9 @@
 
 namespace {
 
+#ifndef SMC_PACKED_ACC
+#define SMC_PACKED_ACC 1
+#endif
 constexpr int kTileW = 256;
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
@@ -99,8 +102,12 @@ __device__ __forceinline__ SmcRec ldg_rec(const unsigned char *row, int pcol) {
     return r;
 }
 
+// (n0, n1) and (n2, den) are 64-bit register pairs: with NG <= 6 record slot 7 holds 1.0f, so (V.z, 1) sits next to each
+// other like (V.x, V.y) and a tap can be accumulated with two FFMA2 instead of three FFMA + one FADD (den + w * 1 rounds
+// exactly like den + w, so the result does not change).  Measured: 8.70 -> 8.38 ms for the scalar-statistics kernel that
+// also filters the film (five sums per tap), 9.90 -> 10.02 ms for the RGB kernel -- so only the former uses it.
 struct Acc {
-    float n0, n1, n2, den;
+    float2 n01, n2d;
     float ns;  // scalar statistics only: the scalar value's sum
     int cnt;
 };
@@ -110,10 +117,10 @@ __device__ __forceinline__ void pair_eval(const SmcCentre<3, NG> &c, const SmcRe
     const bool ok = smc_member<3, NG, MODE>(c, r);
     const float w = smc_weight<3, NG>(c, r, sw);
     if (ok) {
-        a.n0 = __fmaf_rn(w, r.c2.x, a.n0);
-        a.n1 = __fmaf_rn(w, r.c2.y, a.n1);
-        a.n2 = __fmaf_rn(w, r.c1.z, a.n2);
-        a.den = __fadd_rn(a.den, w);
+        a.n01.x = __fmaf_rn(w, r.c2.x, a.n01.x);
+        a.n01.y = __fmaf_rn(w, r.c2.y, a.n01.y);
+        a.n2d.x = __fmaf_rn(w, r.c1.z, a.n2d.x);
+        a.n2d.y = __fadd_rn(a.n2d.y, w);
         // a tap outside the window has sw = -inf -> w = 0: it adds nothing, but must not be counted
         if (COUNT) a.cnt += (sw != -INFINITY) ? 1 : 0;
     }
@@ -127,13 +134,19 @@ __device__ __forceinline__ void pair_eval_c(const SmcCentre<C, NG> &c, const Smc
     const bool ok = smc_member<C, NG, MODE>(c, r);
     const float w = smc_weight<C, NG>(c, r, sw);
     if (ok) {
-        if (C == 3 || FILM) {
-            a.n0 = __fmaf_rn(w, r.c2.x, a.n0);
-            a.n1 = __fmaf_rn(w, r.c2.y, a.n1);
-            a.n2 = __fmaf_rn(w, r.c1.z, a.n2);
+        if (C == 1 && FILM && NG <= 6 && SMC_PACKED_ACC) {
+            const float2 ww = make_float2(w, w);
+            a.n01 = smc_fma2(ww, make_float2(r.c2.x, r.c2.y), a.n01);
+            a.n2d = smc_fma2(ww, make_float2(r.c1.z, r.c1.w), a.n2d);  // slot 7 == 1.0f
+        } else {
+            if (C == 3 || FILM) {
+                a.n01.x = __fmaf_rn(w, r.c2.x, a.n01.x);
+                a.n01.y = __fmaf_rn(w, r.c2.y, a.n01.y);
+                a.n2d.x = __fmaf_rn(w, r.c1.z, a.n2d.x);
+            }
+            a.n2d.y = __fadd_rn(a.n2d.y, w);
         }
         if (C == 1) a.ns = __fmaf_rn(w, r.c1.x, a.ns);
-        a.den = __fadd_rn(a.den, w);
         if (COUNT) a.cnt += (sw != -INFINITY) ? 1 : 0;
     }
 }
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
                 const int yc = min(tc.y0 + ky, p.H - 1), xc = min(xf + kx, p.W - 1);
                 const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, xc + p.padX);
                 smc_make_centre<3, NG, MODE>(rc, cen[ky][kx]);
-                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = 0.f;
+                acc[ky][kx].n01.x = acc[ky][kx].n01.y = acc[ky][kx].n2d.x = acc[ky][kx].n2d.y = 0.f;
                 acc[ky][kx].cnt = 0;
             }
 
@@ -333,16 +346,16 @@ __global__ void __launch_bounds__(kThreads, SMC_STREAM_MINB) filter_stream_kerne
                 Acc a = acc[ky][kx];
                 const SmcRec rc = ldg_rec(img + (size_t)(y + r) * row_bytes, x + p.padX);
                 if (!smc_member<3, NG, MODE>(cen[ky][kx], rc)) {
-                    a.n0 = __fadd_rn(a.n0, rc.c2.x);
-                    a.n1 = __fadd_rn(a.n1, rc.c2.y);
-                    a.n2 = __fadd_rn(a.n2, rc.c1.z);
-                    a.den = __fadd_rn(a.den, 1.f);
+                    a.n01.x = __fadd_rn(a.n01.x, rc.c2.x);
+                    a.n01.y = __fadd_rn(a.n01.y, rc.c2.y);
+                    a.n2d.x = __fadd_rn(a.n2d.x, rc.c1.z);
+                    a.n2d.y = __fadd_rn(a.n2d.y, 1.f);
                     a.cnt += 1;
                 }
                 float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
-                op[0] = __fdiv_rn(a.n0, a.den);
-                op[1] = __fdiv_rn(a.n1, a.den);
-                op[2] = __fdiv_rn(a.n2, a.den);
+                op[0] = __fdiv_rn(a.n01.x, a.n2d.y);
+                op[1] = __fdiv_rn(a.n01.y, a.n2d.y);
+                op[2] = __fdiv_rn(a.n2d.x, a.n2d.y);
                 if (COUNT && p.accepted && p.accepted[tc.z].data)
                     ((int *)(p.accepted[tc.z].data + (size_t)y * p.accepted[tc.z].step))[x] = a.cnt;
             }
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
                 const int yc = min(ti.y0 + ky, p.H - 1), xc = min(xf + kx, p.W - 1);
                 const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, xc + p.padX);
                 smc_make_centre<C, NG, MODE>(rc, cen[ky][kx]);
-                acc[ky][kx].n0 = acc[ky][kx].n1 = acc[ky][kx].n2 = acc[ky][kx].den = acc[ky][kx].ns = 0.f;
+                acc[ky][kx].n01.x = acc[ky][kx].n01.y = acc[ky][kx].n2d.x = acc[ky][kx].n2d.y = acc[ky][kx].ns = 0.f;
                 acc[ky][kx].cnt = 0;
             }
 
@@ -577,25 +590,25 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
                 Acc a = acc[ky][kx];
                 const SmcRec rc = ldg_rec(img + (size_t)(y + r) * row_bytes, x + p.padX);
                 if (!smc_member<C, NG, MODE>(cen[ky][kx], rc)) {
-                    a.n0 = __fadd_rn(a.n0, rc.c2.x);
-                    a.n1 = __fadd_rn(a.n1, rc.c2.y);
-                    a.n2 = __fadd_rn(a.n2, rc.c1.z);
+                    a.n01.x = __fadd_rn(a.n01.x, rc.c2.x);
+                    a.n01.y = __fadd_rn(a.n01.y, rc.c2.y);
+                    a.n2d.x = __fadd_rn(a.n2d.x, rc.c1.z);
                     a.ns = __fadd_rn(a.ns, rc.c1.x);
-                    a.den = __fadd_rn(a.den, 1.f);
+                    a.n2d.y = __fadd_rn(a.n2d.y, 1.f);
                     a.cnt += 1;
                 }
                 if (C == 3) {
                     float *op = (float *)(o.data + (size_t)y * o.step) + x * 3;
-                    op[0] = __fdiv_rn(a.n0, a.den);
-                    op[1] = __fdiv_rn(a.n1, a.den);
-                    op[2] = __fdiv_rn(a.n2, a.den);
+                    op[0] = __fdiv_rn(a.n01.x, a.n2d.y);
+                    op[1] = __fdiv_rn(a.n01.y, a.n2d.y);
+                    op[2] = __fdiv_rn(a.n2d.x, a.n2d.y);
                 } else {
-                    ((float *)(o.data + (size_t)y * o.step))[x] = __fdiv_rn(a.ns, a.den);
+                    ((float *)(o.data + (size_t)y * o.step))[x] = __fdiv_rn(a.ns, a.n2d.y);
                     if (film_out) {
                         float *op = (float *)(p.film_filtered.data + (size_t)y * p.film_filtered.step) + x * 3;
-                        op[0] = __fdiv_rn(a.n0, a.den);
-                        op[1] = __fdiv_rn(a.n1, a.den);
-                        op[2] = __fdiv_rn(a.n2, a.den);
+                        op[0] = __fdiv_rn(a.n01.x, a.n2d.y);
+                        op[1] = __fdiv_rn(a.n01.y, a.n2d.y);
+                        op[2] = __fdiv_rn(a.n2d.x, a.n2d.y);
                     }
                 }
                 if (COUNT && p.accepted && p.accepted[ti.z].data)

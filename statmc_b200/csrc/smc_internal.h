@@ -49,7 +49,7 @@ struct SmcPtrStepSz {
 static_assert(sizeof(SmcPtrStepSz) == 24, "must match cv::cuda::PtrStepSzb");
 
 // ---- packed per-pixel record (64 B) -----------------------------------------------------------------------
-// float slots:  0 m.x  1 m.y  2 d.x  3 d.y | 4 m.z  5 d.z  6 V.z  7 g6 | 8 V.x  9 V.y 10 g0 11 g1 | 12 g2 13 g3 14 g4 15 g5
+// float slots:  0 m.x  1 m.y  2 d.x  3 d.y | 4 m.z  5 d.z  6 V.z  7 g6 (1.0f when NG < 7) | 8 V.x  9 V.y 10 g0 11 g1 | 12 g2 13 g3 14 g4 15 g5
 //   m = Johnson-corrected mean (Welch mode) or raw mean (Moon mode); d = discriminator (Welch) or CI half-width (Moon)
 //   V = value to average (film or film-mean); g* = G-buffer channels pre-scaled by sqrt(-drFactor * log2(e))
 //   channels == 1: m -> slot 0, d -> slot 2, scalar value -> slot 4, film RGB (denoiseFilm, image 0) -> slots 8, 9, 6

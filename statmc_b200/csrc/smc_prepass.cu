@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     constexpr int slots[7] = {10, 11, 12, 13, 14, 15, 7};
 #pragma unroll
     for (int k = 0; k < NG; k++) rec[slots[k]] = __fmul_rn(g[k], p.g_scale[k]);
+    // slot 7 is the seventh G channel; when it is free it holds 1.0f so that (V.z, 1) is a register pair for the streaming
+    // filter's packed accumulation (num.z += w * V.z, den += w * 1 in one FFMA2; smc_filter_stream.cu)
+    if (NG < 7) rec[7] = 1.f;
 
     const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
     unsigned char *row = p.rec + (size_t)z * p.rec_image_stride + (size_t)pr * row_bytes;
