@@ -409,7 +409,9 @@ extern "C" int smc_denoiser_run(smc_denoiser *d) {
 static cudaEvent_t get_event(smc_denoiser *d, size_t i) {
     while (d->events.size() <= i) {
         cudaEvent_t e = nullptr;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        // SMC_PIPE_TRACE=1: events carry timestamps so that smc_denoiser_run_host can print its own timeline
+        static const bool timing = getenv("SMC_PIPE_TRACE") != nullptr;
+        if (cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) return nullptr;
         d->events.push_back(e);
     }
     return d->events[i];
@@ -446,13 +448,52 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
     if (!d->s_in) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
     if (!d->s_out) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
     const int pc = d->ptr_count, H = d->H, r = d->radius;
-    // Chunk boundaries: uniform.  (A schedule that ramps up from a small first chunk and down to a small last one was
-    // measured SLOWER, 14.7 vs 14.1 ms at 4K: a filter launch over few rows fills the persistent grid badly -- one tile is
-    // ~0.3 ms of work for a CTA -- and compute, not PCIe, is then the critical path of the pipeline.)
+    // Chunk boundaries: uniform, except for the last one (below).  (With the earlier, slower filter a schedule that ramped
+    // up from a small first chunk and down to a small last one was measured SLOWER, 14.7 vs 14.1 ms at 4K: a filter launch
+    // over few rows fills the persistent grid badly -- one tile is ~0.35 ms of work for a warp -- and compute, not PCIe, was
+    // then the critical path.  A small FIRST chunk buys nothing in either regime: the bus is busy from t = 0 anyway.)
+    // Chunk schedule: uniform chunks of whole waves of the persistent filter grid (about 8 per frame).  Timeline at 4K
+    // (SMC_PIPE_TRACE=1, profiles/r1g_pipe_trace.txt): the bus delivers a 296-row chunk every 1.71 ms (50.5 GB/s against
+    // 55.6 GB/s for one raw 630 MB copy), the filter needs 1.43 ms for it, so in steady state compute waits for PCIe, and
+    // after the last byte has arrived (12.4 ms) the last full chunk's filter and the remainder's still run (14.05 ms).
+    // SMC_PIPE_TAPER=1 selects a tapered schedule (two-wave first chunk, two-wave and one-wave chunks at the end) meant to
+    // shorten that drain; it is exact (tests pass with it) but measured 13.93 ms against 13.74 ms uniform -- the extra
+    // copies and small launches cost what the shorter drain saves -- so it is off by default.
+    const bool auto_chunks = chunk_rows == 0;
     if (chunk_rows == 0) chunk_rows = auto_chunk_rows(d);
     std::vector<int> bounds;  // chunk k = rows [bounds[k], bounds[k+1])
-    for (int a = 0; a < H; a += chunk_rows) bounds.push_back(a);
-    if (bounds.back() < H) bounds.push_back(H);
+    int unit = 0;             // rows of one wave of the streaming grid
+    if (auto_chunks && d->use_stream) {
+        SmcFilterParams fp;
+        fill_filter_params(d, fp);
+        int tile_w = 256;
+        const int grid = smc_filter_stream_resident_ctas(fp, d->py, ctx->sm_count, &tile_w);
+        const int tiles_x = (d->W + tile_w - 1) / tile_w;
+        unit = (grid / std::max(tiles_x, 1)) * d->py;
+    }
+    const char *tp = getenv("SMC_PIPE_TAPER");
+    const bool taper = unit >= 2 * r && chunk_rows >= 4 * unit && H >= 3 * chunk_rows && (tp && atoi(tp) == 1);
+    if (taper) {
+        // whole waves everywhere but in the first chunk, which takes the remainder: its filter runs while the (longer)
+        // upload of the second chunk is in flight, so a partly filled last wave costs nothing there
+        const int prelast = 2 * unit, last = std::max(unit - (r - 1), 16) & ~1;
+        const int body = H - prelast - last - 2 * unit;   // rows of the middle chunks + the first chunk's remainder
+        const int nw = body / unit;                       // waves to distribute over the middle chunks
+        const int first = 2 * unit + (body - nw * unit);
+        const int nmid = std::max(1, (nw * unit + chunk_rows / 2) / chunk_rows);
+        bounds.push_back(0);
+        int a = first;
+        for (int k = 0; k < nmid; k++) {
+            bounds.push_back(a);
+            a = first + (int)((long long)nw * (k + 1) / nmid) * unit;
+        }
+        bounds.push_back(H - prelast - last);
+        bounds.push_back(H - last);
+        bounds.push_back(H);
+    } else {
+        for (int a = 0; a < H; a += chunk_rows) bounds.push_back(a);
+        if (bounds.back() < H) bounds.push_back(H);
+    }
 
     struct Xfer { const SmcPtrStepSz *dev; smc_plane host; size_t row_bytes; };
     std::vector<Xfer> ups, downs;
@@ -490,6 +531,9 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
     SMC_CUDA(cudaStreamWaitEvent(d->s_in, e_begin, 0));
     SMC_CUDA(cudaStreamWaitEvent(d->s_out, e_begin, 0));
 
+    const bool trace = getenv("SMC_PIPE_TRACE") != nullptr;
+    struct ChunkEv { cudaEvent_t up, pre, filt, down; int a, b, f0, f1; };
+    std::vector<ChunkEv> tr;
     int filtered_to = d->row_begin;  // output rows < filtered_to are done
     for (size_t ci = 0; ci + 1 < bounds.size(); ci++) {
         const int a = bounds[ci], b = bounds[ci + 1];
@@ -503,6 +547,11 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
         SMC_CUDA(cudaStreamWaitEvent(ctx->stream, e_up, 0));
         int rc = prepass_rows(d, a, b);
         if (rc) return rc;
+        cudaEvent_t e_pre = nullptr;
+        if (trace) {
+            e_pre = get_event(d, ev++);
+            if (e_pre) cudaEventRecord(e_pre, ctx->stream);
+        }
         // output row y reads record rows y-r .. y+r-1: complete once rows < b are packed  <=>  y <= b - r
         const int f_end = b == H ? d->row_end : std::min(d->row_end, std::max(filtered_to, b - r + 1));
         const int f_begin = filtered_to;
@@ -521,12 +570,32 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
                                        x.dev->data + (size_t)y0 * x.dev->step, x.dev->step, x.row_bytes, y1 - y0,
                                        cudaMemcpyDeviceToHost, d->s_out));
         }
+        if (trace) {
+            cudaEvent_t e_dn = get_event(d, ev++);
+            if (e_dn) cudaEventRecord(e_dn, d->s_out);
+            tr.push_back({e_up, e_pre, e_f, e_dn, a, b, f_begin, f_end});
+        }
     }
     // join: smc_synchronize(ctx) (or anything queued later on the context stream) covers the downloads
     cudaEvent_t e_end = get_event(d, ev++);
     if (!e_end) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
     SMC_CUDA(cudaEventRecord(e_end, d->s_out));
     SMC_CUDA(cudaStreamWaitEvent(ctx->stream, e_end, 0));
+    if (trace) {  // blocking: a diagnostic, not a mode to run in
+        cudaEventSynchronize(e_end);
+        float t_end = 0.f;
+        cudaEventElapsedTime(&t_end, e_begin, e_end);
+        fprintf(stderr, "smc_denoiser_run_host timeline (ms after the first enqueue), total %.3f\n", t_end);
+        for (const ChunkEv &c : tr) {
+            float u = 0, p = 0, f = 0, dn = 0;
+            cudaEventElapsedTime(&u, e_begin, c.up);
+            if (c.pre) cudaEventElapsedTime(&p, e_begin, c.pre);
+            cudaEventElapsedTime(&f, e_begin, c.filt);
+            if (c.down) cudaEventElapsedTime(&dn, e_begin, c.down);
+            fprintf(stderr, "  rows [%4d,%4d) uploaded %.3f  prepassed %.3f  rows [%4d,%4d) filtered %.3f  downloaded %.3f\n", c.a, c.b,
+                    u, p, c.f0, c.f1, f, dn);
+        }
+    }
     return SMC_OK;
 }
 
