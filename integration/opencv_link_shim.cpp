@@ -12,8 +12,8 @@
 //   cv::cuda::Stream                              OCV/core/src/cuda_stream.cpp -> the smc_context's stream
 //   cv::cuda::stat_denoiser::{setup, synchronize, calculateMeanVars<T>, filter<T>}   CIP/src/stat_denoiser.cpp:90-137,
 //                                                 CIP/src/cuda/stat_denoiser.cu:352-483 -> smc_filter_device_tables & co.
-//   cv::cvtColor (RGB<->BGR only), cv::merge, cv::imwrite / cv::imread (.pfm only)   what buffer.cpp:40-53 and
-//                                                 statpath.cpp:449-453 need to dump / reload statistic planes
+//   cv::cvtColor (RGB<->BGR only), cv::merge, cv::imwrite / cv::imread (.pfm only), cv::glob   what buffer.cpp:40-53 and
+//                                                 statpath.cpp:449-453, 479-481 need to dump / reload statistic planes
 // Everything else of OpenCV that those headers declare is deliberately absent: an accidental new dependency shows up as a
 // link error, not as silently different behaviour.
 //
@@ -21,12 +21,17 @@
 // compiled where a StatMC checkout is present (oracle/Makefile builds it for the parity harness).  One process-wide
 // smc_context on device $STATMC_B200_DEVICE (default 0) backs every GpuMat and Stream, like OpenCV's current device.
 // Errors throw std::runtime_error with smc_last_error() (the reference throws cv::Exception and dies, common.hpp:66-76).
+// -DSMC_SHIM_HOST_ONLY compiles the host half only (cv::Mat, convertTo, cvtColor, merge, imwrite/imread, glob): the parity
+// suite pairs it with a CPU stand-in for the device half (oracle/ref_null_device.cpp) to render fixtures without a GPU.
 #include <opencv2/core.hpp>
 #include <opencv2/core/cuda.hpp>
 #include <opencv2/cudaimgproc.hpp>
 #include <opencv2/imgcodecs.hpp>
 #include <opencv2/imgproc.hpp>
 
+#include <glob.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +61,7 @@ void check(int rc, const char *what) {
     if (rc != SMC_OK) fail(what);
 }
 
+#ifndef SMC_SHIM_HOST_ONLY
 struct Shim {
     smc_context *ctx = nullptr;
     std::mutex mu;
@@ -75,6 +81,8 @@ smc_buffer *owner_of(const void *dev) {
     auto it = s.owner.find(dev);
     return it == s.owner.end() ? nullptr : it->second;
 }
+
+#endif  // SMC_SHIM_HOST_ONLY
 
 // ---- host memory of cv::Mat ------------------------------------------------------------------------------------------
 constexpr size_t kPinnedFrom = 64 << 10;  // planes are pinned so that Buffer::upload/download overlap; tiny tables are not
@@ -163,6 +171,7 @@ const cv::Mat &in_mat(const cv::_InputArray &a) {
     return *static_cast<const cv::Mat *>(a.getObj());
 }
 
+#ifndef SMC_SHIM_HOST_ONLY
 // ---- device memory of cv::cuda::GpuMat ---------------------------------------------------------------------------------
 class ShimAllocator : public cv::cuda::GpuMat::Allocator {
 public:
@@ -215,6 +224,8 @@ Plane2D plane_of(const cv::cuda::GpuMat &g) {
     if (!b) fail("GpuMat memory was not allocated through the shim");
     return {b, (size_t)g.cols * g.elemSize()};
 }
+
+#endif  // SMC_SHIM_HOST_ONLY
 
 }  // namespace
 
@@ -418,6 +429,19 @@ Mat imread(const String &filename, int) {
     return out;
 }
 
+// core glob.cpp, as StatPathIntegrator::Denoise uses it (statpath.cpp:479-481): the files matching a shell pattern, sorted
+void glob(String pattern, std::vector<String> &result, bool recursive) {
+    if (recursive) fail("glob: recursive search is not supported");
+    result.clear();
+    glob_t g;
+    std::memset(&g, 0, sizeof(g));
+    if (::glob(pattern.c_str(), 0, nullptr, &g) == 0)
+        for (size_t i = 0; i < g.gl_pathc; i++) result.emplace_back(g.gl_pathv[i]);
+    ::globfree(&g);
+    std::sort(result.begin(), result.end());
+}
+
+#ifndef SMC_SHIM_HOST_ONLY
 // ========================================================================================================================
 namespace cuda {
 
@@ -580,4 +604,5 @@ SMC_SHIM_INSTANTIATE(::float3)
 
 }  // namespace stat_denoiser
 }  // namespace cuda
+#endif  // SMC_SHIM_HOST_ONLY
 }  // namespace cv

@@ -1,0 +1,59 @@
+"""REAL statistics from the reference's own renderer (BASELINE.json configs[0]), no GPU needed.
+
+* tests/golden/render_veach_mis_16spp.npz -- the reference's veach-mis scene, StatPathIntegrator, 16 spp (4-4-8), rendered by
+  its own code compiled unmodified (oracle/_ref/pbrt_ref_cpu, tools/make_golden_render.py); `film_f` in it was produced by
+  the reference's Estimator::Upload/Denoise/Download flow with the oracle's kernels behind the OpenCV surface.
+* a live run of the same binary on a small scene of ours (tests/render_util.py), when the binary is present.
+Both pin the numpy front-end of the oracle (which the GPU parity tests use) to the reference's dispatch and routing."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import render_util as ru
+from oracle import pyoracle as po
+from util import bits_equal, rel_mad
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_veach_mis_16spp.npz")
+
+
+def _oracle(b, radius, sd, precision):
+    dsf, fac = ru.reference_factors(sd)
+    mc, dc = po.prepass(b["n"], b["mean"], b["m2"], b["m3"])
+    return po.filter(b["film"], [b["normal"], b["albedo"]], fac, radius, dsf, mean_corr=mc, disc=dc, precision=precision)
+
+
+def test_veach_mis_fixture_is_what_the_oracle_computes():
+    z = np.load(GOLDEN)
+    cfg = json.loads(str(z["config"]))
+    b = {k: z[k] for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
+    assert b["n"].shape == (90, 160) and int(b["n"].min()) == int(b["n"].max()) == cfg["spp"] == 16
+    # a path-traced image, not a synthetic one: three lights five orders of magnitude apart, black background pixels
+    assert float(b["film"].max()) > 100 * float(b["film"].mean()) and int((b["m2"].sum(axis=2) == 0).sum()) > 100
+    # Box-Cox statistics: mean of 2 (sqrt(x) - 1) >= -2; the untransformed film-mean is the film up to its colour round trip
+    assert float(b["mean"].min()) >= -2.0 and rel_mad(z["film_mean"], b["film"]) < 1e-4  # film: RGB -> XYZ -> RGB in core/film.cpp
+    assert bits_equal(_oracle(b, cfg["radius"], cfg["sd"], "f32"), z["film_f"])
+    assert rel_mad(_oracle(b, cfg["radius"], cfg["sd"], "f64"), z["film_f"]) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(ru.PBRT_CPU), reason="oracle/_ref/pbrt_ref_cpu not built (needs /root/reference)")
+def test_reference_renderer_runs_and_its_denoise_flow_matches_the_oracle(tmp_path):
+    lut = str(tmp_path / "t005.f32")
+    po.t_table(0.005).tofile(lut)
+    scene, stem = ru.write_scene(tmp_path, width=96, height=64, radius=8, sd=4.0)
+    p = ru.run_pbrt(ru.PBRT_CPU, scene, "--writeimages", env={"STATMC_T_LUT": lut})
+    assert [l for l in p.stdout.splitlines() if l.startswith("SPP: ")] == ["SPP: 4", "SPP: 4", "SPP: 8"]
+    first = {}
+    for spp in (4, 8, 16):
+        b = ru.read_dump(stem, spp)
+        assert int(b["n"].min()) == int(b["n"].max()) == spp
+        assert bits_equal(_oracle(b, 8, 4.0, "f32"), b["film_f"]), spp
+        first[spp] = b["film_f"]
+    # the reference's `--denoise` flow (StatPathIntegrator::Denoise<T>, statpath.cpp:456-550): cv::glob + cv::imread +
+    # convertTo + cvtColor of the dump it has just written, then the same Upload / Denoise / Download
+    for spp in (4, 8, 16):
+        os.remove("%s-%d-film-f.pfm" % (stem, spp))
+    ru.run_pbrt(ru.PBRT_CPU, scene, "--denoise", "--writeimages", env={"STATMC_T_LUT": lut})
+    for spp in (4, 8, 16):
+        assert bits_equal(ru.read_dump(stem, spp)["film_f"], first[spp]), spp

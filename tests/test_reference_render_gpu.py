@@ -1,0 +1,60 @@
+"""REAL statistics from the reference's own renderer on the GPU path.
+
+* the veach-mis fixture (tests/golden/render_veach_mis_16spp.npz, see test_reference_render_cpu.py) through the C ABI;
+* oracle/_ref/pbrt_ref_b200 -- the reference's pbrt-v3 + StatPathIntegrator compiled unmodified and linked against
+  libstatmc_b200.so through integration/opencv_link_shim.cpp -- rendering a small scene of ours on the host cores with
+  every Estimator::Upload / Denoise / Download of its render loop (statpath.cpp:406-418) running on the B200, then its
+  `--denoise` replay of the dump it wrote."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import render_util as ru
+from oracle import pyoracle as po
+from statmc_b200.api import denoise_host
+from util import bits_equal, max_abs, rel_mad
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_veach_mis_16spp.npz")
+
+
+def _oracle64(b, radius, sd):
+    dsf, fac = ru.reference_factors(sd)
+    mc, dc = po.prepass(b["n"], b["mean"], b["m2"], b["m3"])
+    return po.filter(b["film"], [b["normal"], b["albedo"]], fac, radius, dsf, mean_corr=mc, disc=dc, precision="f64"), mc, dc
+
+
+def test_veach_mis_fixture_through_the_c_abi(ctx):
+    z = np.load(GOLDEN)
+    cfg = json.loads(str(z["config"]))
+    b = {k: z[k] for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
+    ref, mc, dc = _oracle64(b, cfg["radius"], cfg["sd"])
+    for kernel in (2, 1):
+        ours = denoise_host(ctx, b, radius=cfg["radius"], sd=cfg["sd"], kernel=kernel, want_aux=True)
+        assert bits_equal(ours["mean_corr"], mc) and bits_equal(ours["disc"], dc)
+        rm = rel_mad(ours["film_f"], ref)
+        print("veach-mis 16 spp (%s): relMAD vs f64 transcription %.2e, max-abs %.2e; vs the reference flow's film-f %.2e"
+              % (ours["kernel"], rm, max_abs(ours["film_f"], ref), rel_mad(ours["film_f"], z["film_f"])))
+        assert rm <= 1e-4 and rel_mad(ours["film_f"], z["film_f"]) <= 1e-4
+
+
+@pytest.mark.skipif(not os.path.exists(ru.PBRT_B200), reason="oracle/_ref/pbrt_ref_b200 not built (needs /root/reference)")
+def test_reference_renderer_on_libstatmc_b200(tmp_path):
+    scene, stem = ru.write_scene(tmp_path, width=160, height=96, radius=10, sd=5.0)
+    p = ru.run_pbrt(ru.PBRT_B200, scene, "--writeimages", nthreads=os.cpu_count() or 8)
+    assert [l for l in p.stdout.splitlines() if l.startswith("SPP: ")] == ["SPP: 4", "SPP: 4", "SPP: 8"]
+    assert sum(l.startswith("CUDA time [ns]: ") for l in p.stdout.splitlines()) == 3
+    first = {}
+    for spp in (4, 8, 16):
+        b = ru.read_dump(stem, spp)
+        assert int(b["n"].min()) == int(b["n"].max()) == spp
+        ref, _, _ = _oracle64(b, 10, 5.0)
+        assert rel_mad(b["film_f"], ref) <= 1e-4, spp
+        first[spp] = b["film_f"]
+    for spp in (4, 8, 16):
+        os.remove("%s-%d-film-f.pfm" % (stem, spp))
+    ru.run_pbrt(ru.PBRT_B200, scene, "--denoise", "--writeimages")
+    for spp in (4, 8, 16):
+        assert bits_equal(ru.read_dump(stem, spp)["film_f"], first[spp]), spp

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""tests/golden/render_veach_mis_16spp.npz: REAL statistics from the reference's own renderer (BASELINE.json configs[0]).
+
+oracle/_ref/pbrt_ref_cpu is the reference's pbrt-v3 + StatPathIntegrator, every source compiled unmodified (oracle/Makefile
+target `pbrt`), linked against the host half of integration/opencv_link_shim.cpp and a CPU stand-in for the device half
+(oracle/ref_null_device.cpp, which runs the oracle's restatement of the kernels).  This script renders the reference's
+scenes/veach-mis/scene-stat.pbrt with scenes/render-denoise.pbrt as the active integrator configuration -- 16 spp in the
+4-4-8 schedule, multichannel statistics, denoiseimage, r = 20, sd = 10, G-buffers albedo 0.02 / normal 0.1 -- at a reduced
+film size (fixture size; the only edits are the film resolution, the output path, `iterations` 13 -> 3 and the output
+regex), and stores the dumped planes of the last iteration.  Runs in the build container only (needs /root/reference).
+
+    python tools/make_golden_render.py [--width 160 --height 90]
+"""
+import argparse
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from statmc_b200 import pfm  # noqa: E402
+
+REF = "/root/reference"
+EXE = os.path.join(ROOT, "oracle", "_ref", "pbrt_ref_cpu")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=160)
+    ap.add_argument("--height", type=int, default=90)
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "render_veach_mis_16spp.npz"))
+    a = ap.parse_args()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "scenes", "veach-mis"))
+        os.makedirs(os.path.join(tmp, "out"))
+        s = open(os.path.join(REF, "scenes", "veach-mis", "scene-stat.pbrt")).read()
+        res = '"integer xresolution" [ 1280 ] "integer yresolution" [ 720 ]'
+        name = '"string filename" [ "veach-mis.pfm" ]'
+        assert res in s and name in s
+        s = s.replace(res, '"integer xresolution" [ %d ] "integer yresolution" [ %d ]' % (a.width, a.height))
+        s = s.replace(name, '"string filename" [ "%s/out/veach-mis.pfm" ]' % tmp)
+        open(os.path.join(tmp, "scenes", "veach-mis", "scene-stat.pbrt"), "w").write(s)
+        c = open(os.path.join(REF, "scenes", "render-denoise.pbrt")).read()
+        it, rx = '"integer  iterations"         [13]', '"string   outputregex"  ["film|film-f"]'
+        assert it in c and rx in c
+        c = c.replace(it, '"integer  iterations"         [3]').replace(rx, '"string   outputregex"  [".*"]')
+        open(os.path.join(tmp, "scenes", "_active.pbrt"), "w").write(c)  # scene-stat.pbrt: Include "../_active.pbrt"
+        lut = os.path.join(tmp, "t005.f32")
+        po.t_table(0.005).tofile(lut)
+        p = subprocess.run([EXE, "--writeimages", "--nthreads", "8", "scene-stat.pbrt"], text=True, capture_output=True,
+                           cwd=os.path.join(tmp, "scenes", "veach-mis"), env=dict(os.environ, STATMC_T_LUT=lut))
+        assert p.returncode == 0, p.stdout + p.stderr
+        st = os.path.join(tmp, "out", "veach-mis-16-")
+        rd = lambda k, dt=np.float32: pfm.read(st + k + ".pfm", dt) if dt is not np.float32 else pfm.read(st + k + ".pfm")
+        z = {"n": rd("t0-b0-n", np.int32), "mean": rd("t0-b0-mean"), "m2": rd("t0-b0-m2"), "m3": rd("t0-b0-m3"),
+             "film_mean": rd("t0-b0-film-mean"), "film_m2": rd("t0-b0-film-m2"), "film": rd("film"),
+             "normal": rd("t1-b0-film-mean"), "albedo": rd("t2-b0-film-mean"), "film_f": rd("film-f")}
+        assert int(z["n"].min()) == 16 and int(z["n"].max()) == 16
+        z["config"] = np.array('{"scene": "veach-mis/scene-stat.pbrt + render-denoise.pbrt", "spp": 16, "radius": 20, "sd": 10.0, '
+                               '"normal_sd": 0.1, "albedo_sd": 0.02, "film_f": "reference Estimator flow, kernels = oracle f32"}')
+        np.savez_compressed(a.out, **z)
+        print(a.out, os.path.getsize(a.out), "bytes;", p.stdout.count("Iteration:"), "iterations")
+
+
+if __name__ == "__main__":
+    main()
