@@ -15,7 +15,10 @@ import render_util as ru
 from oracle import pyoracle as po
 from util import bits_equal, rel_mad
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_veach_mis_16spp.npz")
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# veach-mis from the reference's own renderer: 16 spp (BASELINE configs[0]), 256 spp (t-table index 509; configs[1]'s sample
+# count) and 4096 spp with the glass-caustics filter parameters r 6 / sd 3 (table clamp at index 1023; configs[4]'s)
+RENDERS = ["render_veach_mis_16spp.npz", "render_veach_mis_256spp.npz", "render_veach_mis_4096spp.npz"]
 
 
 def _oracle(b, radius, sd, precision):
@@ -24,13 +27,14 @@ def _oracle(b, radius, sd, precision):
     return po.filter(b["film"], [b["normal"], b["albedo"]], fac, radius, dsf, mean_corr=mc, disc=dc, precision=precision)
 
 
-def test_veach_mis_fixture_is_what_the_oracle_computes():
-    z = np.load(GOLDEN)
+@pytest.mark.parametrize("name", RENDERS)
+def test_veach_mis_fixture_is_what_the_oracle_computes(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
     cfg = json.loads(str(z["config"]))
     b = {k: z[k] for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
-    assert b["n"].shape == (90, 160) and int(b["n"].min()) == int(b["n"].max()) == cfg["spp"] == 16
+    assert int(b["n"].min()) == int(b["n"].max()) == cfg["spp"] and "%dspp" % cfg["spp"] in name
     # a path-traced image, not a synthetic one: three lights five orders of magnitude apart, black background pixels
-    assert float(b["film"].max()) > 100 * float(b["film"].mean()) and int((b["m2"].sum(axis=2) == 0).sum()) > 100
+    assert float(b["film"].max()) > 100 * float(b["film"].mean()) and int((b["m2"].sum(axis=2) == 0).sum()) > 50
     # Box-Cox statistics: mean of 2 (sqrt(x) - 1) >= -2; the untransformed film-mean is the film up to its colour round trip
     assert float(b["mean"].min()) >= -2.0 and rel_mad(z["film_mean"], b["film"]) < 1e-4  # film: RGB -> XYZ -> RGB in core/film.cpp
     assert bits_equal(_oracle(b, cfg["radius"], cfg["sd"], "f32"), z["film_f"])

@@ -17,7 +17,10 @@ from statmc_b200.api import denoise_host
 from util import bits_equal, max_abs, rel_mad
 
 pytestmark = pytest.mark.gpu
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_veach_mis_16spp.npz")
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# veach-mis from the reference's own renderer: 16 spp (BASELINE configs[0]), 256 spp (t-table index 509; configs[1]'s sample
+# count) and 4096 spp with the glass-caustics filter parameters r 6 / sd 3 (table clamp at index 1023; configs[4]'s)
+RENDERS = ["render_veach_mis_16spp.npz", "render_veach_mis_256spp.npz", "render_veach_mis_4096spp.npz"]
 
 
 def _oracle64(b, radius, sd):
@@ -26,8 +29,9 @@ def _oracle64(b, radius, sd):
     return po.filter(b["film"], [b["normal"], b["albedo"]], fac, radius, dsf, mean_corr=mc, disc=dc, precision="f64"), mc, dc
 
 
-def test_veach_mis_fixture_through_the_c_abi(ctx):
-    z = np.load(GOLDEN)
+@pytest.mark.parametrize("name", RENDERS)
+def test_veach_mis_fixture_through_the_c_abi(ctx, name):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
     cfg = json.loads(str(z["config"]))
     b = {k: z[k] for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
     ref, mc, dc = _oracle64(b, cfg["radius"], cfg["sd"])
@@ -35,8 +39,8 @@ def test_veach_mis_fixture_through_the_c_abi(ctx):
         ours = denoise_host(ctx, b, radius=cfg["radius"], sd=cfg["sd"], kernel=kernel, want_aux=True)
         assert bits_equal(ours["mean_corr"], mc) and bits_equal(ours["disc"], dc)
         rm = rel_mad(ours["film_f"], ref)
-        print("veach-mis 16 spp (%s): relMAD vs f64 transcription %.2e, max-abs %.2e; vs the reference flow's film-f %.2e"
-              % (ours["kernel"], rm, max_abs(ours["film_f"], ref), rel_mad(ours["film_f"], z["film_f"])))
+        print("veach-mis %d spp (%s): relMAD vs f64 transcription %.2e, max-abs %.2e; vs the reference flow's film-f %.2e"
+              % (cfg["spp"], ours["kernel"], rm, max_abs(ours["film_f"], ref), rel_mad(ours["film_f"], z["film_f"])))
         assert rm <= 1e-4 and rel_mad(ours["film_f"], z["film_f"]) <= 1e-4
 
 

@@ -9,7 +9,10 @@ scenes/veach-mis/scene-stat.pbrt with scenes/render-denoise.pbrt as the active i
 film size (fixture size; the only edits are the film resolution, the output path, `iterations` 13 -> 3 and the output
 regex), and stores the dumped planes of the last iteration.  Runs in the build container only (needs /root/reference).
 
-    python tools/make_golden_render.py [--width 160 --height 90]
+    python tools/make_golden_render.py                                       # 160 x 90, 16 spp   (configs[0])
+    python tools/make_golden_render.py --width 80 --height 45 --iterations 7   # 256 spp: t-table index 509 (configs[1]'s spp)
+    python tools/make_golden_render.py --width 80 --height 45 --iterations 11 --config render-denoise-glass-caustics.pbrt
+                                                                             # 4096 spp, r 6 / sd 3: table clamp (configs[4]'s)
 """
 import argparse
 import os
@@ -32,8 +35,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--width", type=int, default=160)
     ap.add_argument("--height", type=int, default=90)
-    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "render_veach_mis_16spp.npz"))
+    ap.add_argument("--iterations", type=int, default=3, help="4 << (iterations - 1) spp in total (expiterations)")
+    ap.add_argument("--config", default="render-denoise.pbrt",
+                    help="integrator configuration of the reference: render-denoise.pbrt (r 20, sd 10) or "
+                         "render-denoise-glass-caustics.pbrt (r 6, sd 3)")
+    ap.add_argument("--out", default="")
     a = ap.parse_args()
+    spp = 4 << (a.iterations - 1)
+    if not a.out:
+        a.out = os.path.join(ROOT, "tests", "golden", "render_veach_mis_%dspp.npz" % spp)
     with tempfile.TemporaryDirectory() as tmp:
         os.makedirs(os.path.join(tmp, "scenes", "veach-mis"))
         os.makedirs(os.path.join(tmp, "out"))
@@ -44,24 +54,28 @@ def main():
         s = s.replace(res, '"integer xresolution" [ %d ] "integer yresolution" [ %d ]' % (a.width, a.height))
         s = s.replace(name, '"string filename" [ "%s/out/veach-mis.pfm" ]' % tmp)
         open(os.path.join(tmp, "scenes", "veach-mis", "scene-stat.pbrt"), "w").write(s)
-        c = open(os.path.join(REF, "scenes", "render-denoise.pbrt")).read()
+        c = open(os.path.join(REF, "scenes", a.config)).read()
         it, rx = '"integer  iterations"         [13]', '"string   outputregex"  ["film|film-f"]'
         assert it in c and rx in c
-        c = c.replace(it, '"integer  iterations"         [3]').replace(rx, '"string   outputregex"  [".*"]')
+        c = c.replace(it, '"integer  iterations"         [%d]' % a.iterations).replace(rx, '"string   outputregex"  [".*"]')
+        import re
+        radius = int(re.search(r'"integer\s+filterradius"\s+\[(\d+)\]', c).group(1))
+        sd = float(re.search(r'"float\s+filtersd"\s+\[([0-9.]+)\]', c).group(1))
         open(os.path.join(tmp, "scenes", "_active.pbrt"), "w").write(c)  # scene-stat.pbrt: Include "../_active.pbrt"
         lut = os.path.join(tmp, "t005.f32")
         po.t_table(0.005).tofile(lut)
         p = subprocess.run([EXE, "--writeimages", "--nthreads", "8", "scene-stat.pbrt"], text=True, capture_output=True,
                            cwd=os.path.join(tmp, "scenes", "veach-mis"), env=dict(os.environ, STATMC_T_LUT=lut))
         assert p.returncode == 0, p.stdout + p.stderr
-        st = os.path.join(tmp, "out", "veach-mis-16-")
+        st = os.path.join(tmp, "out", "veach-mis-%d-" % spp)
         rd = lambda k, dt=np.float32: pfm.read(st + k + ".pfm", dt) if dt is not np.float32 else pfm.read(st + k + ".pfm")
         z = {"n": rd("t0-b0-n", np.int32), "mean": rd("t0-b0-mean"), "m2": rd("t0-b0-m2"), "m3": rd("t0-b0-m3"),
              "film_mean": rd("t0-b0-film-mean"), "film_m2": rd("t0-b0-film-m2"), "film": rd("film"),
              "normal": rd("t1-b0-film-mean"), "albedo": rd("t2-b0-film-mean"), "film_f": rd("film-f")}
-        assert int(z["n"].min()) == 16 and int(z["n"].max()) == 16
-        z["config"] = np.array('{"scene": "veach-mis/scene-stat.pbrt + render-denoise.pbrt", "spp": 16, "radius": 20, "sd": 10.0, '
-                               '"normal_sd": 0.1, "albedo_sd": 0.02, "film_f": "reference Estimator flow, kernels = oracle f32"}')
+        assert int(z["n"].min()) == spp and int(z["n"].max()) == spp
+        z["config"] = np.array('{"scene": "veach-mis/scene-stat.pbrt + %s", "spp": %d, "radius": %d, "sd": %.1f, '
+                               '"normal_sd": 0.1, "albedo_sd": 0.02, "film_f": "reference Estimator flow, kernels = oracle f32"}'
+                               % (a.config, spp, radius, sd))
         np.savez_compressed(a.out, **z)
         print(a.out, os.path.getsize(a.out), "bytes;", p.stdout.count("Iteration:"), "iterations")
 
