@@ -16,8 +16,9 @@ PBRT_B200 = os.path.join(ROOT, "oracle", "_ref", "pbrt_ref_b200")
 # reference's scenes/render-denoise.pbrt parameters (statpath.cpp:902-1020 reads them).
 SCENE = """
 Integrator "statpath"
-  "integer maxdepth" [16] "bool expiterations" ["true"] "integer iterations" [{iterations}] "integer trackedbounces" [0]
-  "bool multichannelstats" ["true"] "bool denoiseimage" ["true"] "bool acrr" ["false"] "bool smis" ["false"]
+  "integer maxdepth" [16] "bool expiterations" ["true"] "integer iterations" [{iterations}]
+  "integer trackedbounces" [{trackedbounces}] "bool multichannelstats" ["{multichannelstats}"]
+  "bool denoiseimage" ["{denoiseimage}"] "bool acrr" ["{acrr}"] "bool smis" ["{smis}"]
   "bool calcstats" ["false"] "bool calcprodenstats" ["false"] "bool calcmoonstats" ["false"] "bool calcgbuffers" ["false"]
   "bool calcitstats" ["false"]
   "float filtersd" [{sd}] "integer filterradius" [{radius}]
@@ -61,12 +62,28 @@ WorldEnd
 """
 
 
-def write_scene(directory, width=96, height=64, radius=8, sd=4.0, iterations=3):
+def write_scene(directory, width=96, height=64, radius=8, sd=4.0, iterations=3, trackedbounces=0, multichannelstats=True,
+                denoiseimage=True, acrr=False, smis=False):
+    """scenes/render-denoise.pbrt by default; acrr.pbrt = trackedbounces 5, multichannelstats / denoiseimage false, acrr true;
+    smis.pbrt = trackedbounces 6, multichannelstats / denoiseimage false, smis true."""
     stem = os.path.join(str(directory), "smc")
     path = os.path.join(str(directory), "scene.pbrt")
+    b = lambda v: "true" if v else "false"
     with open(path, "w") as f:
-        f.write(SCENE.format(width=width, height=height, radius=radius, sd=sd, iterations=iterations, stem=stem))
+        f.write(SCENE.format(width=width, height=height, radius=radius, sd=sd, iterations=iterations, stem=stem,
+                             trackedbounces=trackedbounces, multichannelstats=b(multichannelstats),
+                             denoiseimage=b(denoiseimage), acrr=b(acrr), smis=b(smis)))
     return path, stem
+
+
+def read_planes(stem, spp, type_index, bounce, channels):
+    """Statistic planes of type `type_index`, bounce `bounce` (scalar planes come back H x W)."""
+    pre = "%s-%d-t%d-b%d-" % (stem, spp, type_index, bounce)
+    rd = lambda k: pfm.read(pre + k + ".pfm")
+    sq = (lambda a: a[..., 0] if a.ndim == 3 and channels == 1 else a)
+    out = {k.replace("-", "_"): sq(rd(k)) for k in ("mean", "m2", "m3", "film-mean", "film-mean-f")}
+    out["n"] = pfm.read(pre + "n.pfm", np.int32)
+    return out
 
 
 def run_pbrt(exe, scene, *flags, env=None, nthreads=8):

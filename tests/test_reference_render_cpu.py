@@ -61,3 +61,37 @@ def test_reference_renderer_runs_and_its_denoise_flow_matches_the_oracle(tmp_pat
     ru.run_pbrt(ru.PBRT_CPU, scene, "--denoise", "--writeimages", env={"STATMC_T_LUT": lut})
     for spp in (4, 8, 16):
         assert bits_equal(ru.read_dump(stem, spp)["film_f"], first[spp]), spp
+
+
+@pytest.mark.skipif(not os.path.exists(ru.PBRT_CPU), reason="oracle/_ref/pbrt_ref_cpu not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", ["acrr", "smis"])
+def test_reference_renderer_acrr_and_smis_configurations(tmp_path, mode):
+    """scenes/acrr.pbrt and scenes/smis.pbrt of the reference: scalar statistics per tracked bounce, one filter<float> launch
+    over all of them (no film), and the filtered planes feed the NEXT iteration's Russian roulette / MIS decisions
+    (statpath.cpp:306-313) -- the feedback loop runs here with the oracle's kernels in it."""
+    from statmc_b200 import pfm
+    lut = str(tmp_path / "t005.f32")
+    po.t_table(0.005).tofile(lut)
+    nb = 5 if mode == "acrr" else 6
+    scene, stem = ru.write_scene(tmp_path, width=80, height=48, radius=6, sd=3.0, trackedbounces=nb, multichannelstats=False,
+                                 denoiseimage=False, acrr=mode == "acrr", smis=mode == "smis")
+    ru.run_pbrt(ru.PBRT_CPU, scene, "--writeimages", env={"STATMC_T_LUT": lut})
+    dsf, fac = ru.reference_factors(3.0)
+    # statistic types in the order CreateStatPathIntegrator enables them (statpath.cpp:1026-1160)
+    # acrr: t0 = radiance per bounce, t1 / t2 = normal / albedo;  smis alone: no radiance statistics at all, t0 / t1 = BSDF /
+    # light win rates per bounce, t2 / t3 = normal / albedo
+    filtered = [0] if mode == "acrr" else [0, 1]
+    i_normal = 1 if mode == "acrr" else 2
+    normal = pfm.read("%s-16-t%d-b0-film-mean.pfm" % (stem, i_normal))
+    albedo = pfm.read("%s-16-t%d-b0-film-mean.pfm" % (stem, i_normal + 1))
+    assert normal.shape == (48, 80, 3) and float(np.abs(normal).max()) <= 1.0 + 1e-6
+    checked = 0
+    for t in filtered:
+        for j in range(nb):
+            pl = ru.read_planes(stem, 16, t, j, 1)
+            assert pl["n"].shape == (48, 80)
+            mc, dc = po.prepass(pl["n"], pl["mean"], pl["m2"], pl["m3"])
+            ref = po.filter(pl["film_mean"], [normal, albedo], fac, 6, dsf, mean_corr=mc, disc=dc, precision="f32")
+            assert bits_equal(ref, pl["film_mean_f"]), (t, j)
+            checked += 1
+    assert checked == len(filtered) * nb
