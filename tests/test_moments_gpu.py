@@ -258,3 +258,32 @@ def test_accumulate_vs_reference_estimator_live_720p_band(ctx):
           "values differ in the last bit(s) (sqrtf vs powf)"
           % ({k: "%.1e" % v for k, v in worst.items()}, {k: "%.1e" % v for k, v in own.items()}, differing,
              5 * got["mean"].size))
+
+
+def test_accumulate_on_the_reference_renderers_real_samples(ctx):
+    """smc_accumulate on the REAL radiance sample stream of the reference's renderer (veach-mis, 16 spp in the 4-4-8 schedule;
+    tests/golden/render_veach_mis_16spp_samples.npz) against the planes the renderer's own accumulation produced: bit-identical
+    to the sqrtf restatement, untransformed film moments bit-identical to the reference, Box-Cox moments within four times the
+    first-order effect of a 1-ulp change of the transformed samples (sqrtf vs libm powf; 0.3 % of the values differ at all)."""
+    from util import one_ulp_input_bound, real_sample_fixture
+    smp, ref = real_sample_fixture()
+    S, H, W, _ = smp.shape
+    st = MomentState(ctx, W, H, 3, transform=True)
+    ora = po.new_state(H, W)
+    for lo, hi in ((0, 4), (4, 8), (8, 16)):
+        st.add_samples(np.ascontiguousarray(smp[lo:hi]))
+        po.accumulate(ora, smp[lo:hi], transform=True, use_sqrt=True)
+    got = st.download()
+    assert np.array_equal(got["n"], ref["n"].astype(np.int32))
+    for k in PLANES:
+        assert bits_equal(got[k], ora[k]), k
+    assert bits_equal(got["film_mean"], ref["film_mean"]) and bits_equal(got["film_m2"], ref["film_m2"])
+    bound = one_ulp_input_bound(smp)
+    worst = {}
+    for k in ("mean", "m2", "m3"):
+        err = np.abs(got[k].astype(np.float64) - ref[k])
+        worst[k] = float((err / np.maximum(bound[k], 1e-300)).max())
+        assert np.all(err <= 4.0 * bound[k] + 1e-30), (k, worst[k])
+    differing = sum(int((got[k].view(np.uint32) != ref[k].view(np.uint32)).sum()) for k in PLANES)
+    print("real samples vs the reference renderer's planes: %d of %d values differ; worst error / 1-ulp-input bound %s"
+          % (differing, 5 * got["mean"].size, {k: "%.2f" % v for k, v in worst.items()}))

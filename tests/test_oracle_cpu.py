@@ -240,3 +240,32 @@ def test_reference_tile_pixel_layout():
     # estimator.h:115-124: {u64 n; T mean, m2, m3, filmMean, filmM2} aligned(64) -> 128 B (Vec3) / 64 B (Float)
     assert po.ref_tile_pixel_layout(3) == (128, 64)
     assert po.ref_tile_pixel_layout(1) == (64, 64)
+
+
+def test_accumulate_oracle_on_the_reference_renderers_real_samples():
+    """The radiance samples the reference's path tracer produced for veach-mis (logged by a forced-include hook in front of
+    its accumulation, statpath.cpp compiled unmodified) replayed through the restatement: every plane the renderer dumped
+    (its own StatTile code inside the render loop, Merge*Tile into the planes, PFM out and back) comes out bit for bit.
+    The sqrtf variant -- what the CUDA kernel computes -- stays within four times the first-order effect of a 1-ulp change of the inputs (the rest: the state updates round differently afterwards)."""
+    from util import bits_equal, one_ulp_input_bound, real_sample_fixture
+    smp, ref = real_sample_fixture()
+    S, H, W, _ = smp.shape
+    assert S == 16 and float(smp.max()) > 1000 and float((smp == 0).mean()) > 0.01  # light hits and black paths
+    st = po.new_state(H, W)
+    for lo, hi in ((0, 4), (4, 8), (8, 16)):  # the render loop's 4-4-8 schedule
+        po.accumulate(st, smp[lo:hi], transform=True)
+    assert np.array_equal(st["n"], ref["n"])
+    for k in PLANES:
+        assert bits_equal(st[k], ref[k]), k
+    sq = po.new_state(H, W)
+    po.accumulate(sq, smp, transform=True, use_sqrt=True)
+    bound = one_ulp_input_bound(smp)
+    for k in ("mean", "m2", "m3"):
+        err = np.abs(sq[k].astype(np.float64) - ref[k])
+        assert np.all(err <= 4.0 * bound[k] + 1e-30), (k, float((err / np.maximum(bound[k], 1e-300)).max()))
+    assert bits_equal(sq["film_mean"], ref["film_mean"]) and bits_equal(sq["film_m2"], ref["film_m2"])  # no transform there
+    if po.ref_accum_available():  # and the compiled estimator.h harness agrees with the renderer it was taken from
+        h = po.new_state(H, W)
+        po.ref_accumulate(h, smp, transform=True)
+        for k in PLANES:
+            assert bits_equal(h[k], ref[k]), k

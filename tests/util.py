@@ -72,3 +72,27 @@ def accum_scale(state):
     sigma = np.where(m2 > 0, sigma, np.maximum(mean, 1e-30))
     fsigma = np.where(fm2 > 0, fsigma, np.maximum(mean, 1e-30))
     return {"mean": sigma, "m2": n * sigma ** 2, "m3": n * sigma ** 3, "film_mean": fsigma, "film_m2": n * fsigma ** 2}
+
+
+def real_sample_fixture():
+    """tests/golden/render_veach_mis_16spp_samples.npz: the radiance sample stream of the reference's own renderer on its
+    veach-mis scene (16 spp, 80 x 45; tools/make_golden_render.py --samples) and the statistic planes its own accumulation
+    code made of it.  -> samples [S][H][W][3], reference state dict (n int64)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "render_veach_mis_16spp_samples.npz"))
+    ref = {k: z[k] for k in PLANES}
+    ref["n"] = z["n"].astype(np.int64)
+    return z["samples"], ref
+
+
+def one_ulp_input_bound(samples):
+    """First-order effect on (mean, M2, M3) of the Box-Cox statistics of moving every TRANSFORMED sample by one float32 ulp
+    (float64 arithmetic): what replacing libm's powf(x, .5f) by sqrtf(x) -- 1 ulp apart for 6e-4 of inputs -- can do at most,
+    pixel by pixel.  d mean / dx_i = 1/n,  d M2 / dx_i = 2 d_i,  d M3 / dx_i = 3 d_i^2 - 3 M2 / n."""
+    x = 2.0 * (np.sqrt(samples.astype(np.float64)) - 1.0)
+    ulp = np.spacing(np.abs(x).astype(np.float32)).astype(np.float64)
+    n = x.shape[0]
+    d = x - x.mean(axis=0)
+    m2 = (d * d).sum(axis=0)
+    return {"mean": ulp.sum(axis=0) / n, "m2": (2.0 * np.abs(d) * ulp).sum(axis=0),
+            "m3": (np.abs(3.0 * d * d - 3.0 * m2 / n) * ulp).sum(axis=0)}

@@ -13,6 +13,7 @@ regex), and stores the dumped planes of the last iteration.  Runs in the build c
     python tools/make_golden_render.py --width 80 --height 45 --iterations 7   # 256 spp: t-table index 509 (configs[1]'s spp)
     python tools/make_golden_render.py --width 80 --height 45 --iterations 11 --config render-denoise-glass-caustics.pbrt
                                                                              # 4096 spp, r 6 / sd 3: table clamp (configs[4]'s)
+    python tools/make_golden_render.py --width 80 --height 45 --samples      # 16 spp + the per-pixel radiance sample stream
 """
 import argparse
 import os
@@ -39,11 +40,15 @@ def main():
     ap.add_argument("--config", default="render-denoise.pbrt",
                     help="integrator configuration of the reference: render-denoise.pbrt (r 20, sd 10) or "
                          "render-denoise-glass-caustics.pbrt (r 6, sd 3)")
+    ap.add_argument("--samples", action="store_true",
+                    help="also store the radiance sample stream [S][H][W][3] logged by oracle/_ref/pbrt_ref_cpu_samplelog (the "
+                         "same renderer with a forced-include hook in front of the reference's accumulation) -> "
+                         "render_veach_mis_<spp>spp_samples.npz")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     spp = 4 << (a.iterations - 1)
     if not a.out:
-        a.out = os.path.join(ROOT, "tests", "golden", "render_veach_mis_%dspp.npz" % spp)
+        a.out = os.path.join(ROOT, "tests", "golden", "render_veach_mis_%dspp%s.npz" % (spp, "_samples" if a.samples else ""))
     with tempfile.TemporaryDirectory() as tmp:
         os.makedirs(os.path.join(tmp, "scenes", "veach-mis"))
         os.makedirs(os.path.join(tmp, "out"))
@@ -76,6 +81,22 @@ def main():
         z["config"] = np.array('{"scene": "veach-mis/scene-stat.pbrt + %s", "spp": %d, "radius": %d, "sd": %.1f, '
                                '"normal_sd": 0.1, "albedo_sd": 0.02, "film_f": "reference Estimator flow, kernels = oracle f32"}'
                                % (a.config, spp, radius, sd))
+        if a.samples:
+            # the logging build renders the same image (the render is deterministic) and writes every radiance sample
+            logf = os.path.join(tmp, "samples.f32")
+            for k in os.listdir(os.path.join(tmp, "out")):
+                os.remove(os.path.join(tmp, "out", k))
+            env = dict(os.environ, STATMC_T_LUT=lut, STATMC_SAMPLE_LOG=logf, STATMC_SAMPLE_LOG_W=str(a.width),
+                       STATMC_SAMPLE_LOG_H=str(a.height), STATMC_SAMPLE_LOG_S=str(spp))
+            p2 = subprocess.run([EXE + "_samplelog", "--writeimages", "--nthreads", "8", "scene-stat.pbrt"], text=True,
+                                capture_output=True, cwd=os.path.join(tmp, "scenes", "veach-mis"), env=env)
+            assert p2.returncode == 0, p2.stdout + p2.stderr
+            for k in ("mean", "m2", "m3", "film-mean", "film-m2"):
+                again = rd("t0-b0-" + k)
+                assert np.array_equal(again.view(np.uint32), z[k.replace("-", "_")].view(np.uint32)), k
+            z["samples"] = np.fromfile(logf, np.float32).reshape(spp, a.height, a.width, 3)
+            for k in ("film", "normal", "albedo", "film_f"):  # the denoiser fixtures carry those
+                del z[k]
         np.savez_compressed(a.out, **z)
         print(a.out, os.path.getsize(a.out), "bytes;", p.stdout.count("Iteration:"), "iterations")
 
