@@ -162,7 +162,8 @@ void mat_create2d(cv::Mat &m, int rows, int cols, int type) {  // `m` must hold 
 cv::Mat &out_mat(const cv::_OutputArray &a, int rows, int cols, int type) {
     if ((a.getFlags() & cv::_InputArray::KIND_MASK) != cv::_InputArray::MAT) fail("only cv::Mat output arrays are supported");
     cv::Mat &m = *static_cast<cv::Mat *>(a.getObj());
-    if (m.dims != 2 || m.rows != rows || m.cols != cols || m.type() != (type & cv::Mat::TYPE_MASK) || (!m.data && rows * cols))
+    if (m.dims != 2 || m.rows != rows || m.cols != cols || m.type() != (int)(type & cv::Mat::TYPE_MASK) ||
+        (!m.data && rows > 0 && cols > 0))
         m = cv::Mat(rows, cols, type);
     return m;
 }
