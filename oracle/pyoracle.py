@@ -155,7 +155,8 @@ def filter(value: np.ndarray, gbufs, gbuf_dr_factors, radius: int, ds_factor: fl
     if want_accepted:
         a.accepted = C.pointer(_pl(acc))
     a.mode = mode
-    (_lib.smo_filter_f64 if precision == "f64" else _lib.smo_filter_f32)(C.byref(a))
+    # "sym64": the symmetric pair-evaluation prototype (every unordered pair once; statmc_oracle.c smo_filter_sym_f64)
+    {"f64": _lib.smo_filter_f64, "f32": _lib.smo_filter_f32, "sym64": _lib.smo_filter_sym_f64}[precision](C.byref(a))
     return (out, acc) if want_accepted else out
 
 

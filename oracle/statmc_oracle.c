@@ -31,6 +31,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define SMO_LUT_SIZE 1024 /* SD.cu:43 T_QUANTILE_LUT_SIZE */
@@ -401,4 +402,79 @@ void smo_merge_moments_f64(int64_t npix, int C, const int64_t *nA, const double 
                      3.0 * d * (na * m2B[i] - nb * m2A[i]) / nn;
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PROTOTYPE (DESIGN.md "what comes next" item 1): the filter with every unordered pair of positions evaluated ONCE.
+ *
+ * Membership (SD.cu:81-88) and the weight (SD.cu:90-112, :261) are symmetric in (C, I), so for a forward offset
+ * (dy, dx) -- dy == 0 and dx in [1, r], or dy in [1, r] and dx in [-r, r], inside the disc -- the pair P, Q = P + (dy, dx)
+ * is evaluated once and contributes  w * V(Q) to P  when (dy, dx) is a tap of P's half-open window (dy <= r-1, dx <= r-1),
+ * and  w * V(P) to Q  when (-dy, -dx) is a tap of Q's (dx >= -(r-1)).  Replicated borders: P and Q range over the image
+ * extended by r on every side, their records are the clamped ones (BrdReplicate), and only positions inside the image
+ * receive anything.  Sums in double: the result differs from smo_filter_f64 only by the order of summation, which is what
+ * tests/test_oracle_cpu.py::test_symmetric_pair_evaluation_prototype asserts.  Mode 0 (Welch) only: the Moon test is not
+ * symmetric.  Single-threaded over rows of P with per-thread row accumulators merged at the end (simple, not fast).
+ * ------------------------------------------------------------------------------------------ */
+void smo_filter_sym_f64(const smo_filter_args *a) {
+    const int W = a->W, H = a->H, C = a->C, VC = a->value_channels, rad = a->radius, rad2 = rad * rad;
+    double *num = (double *)calloc((size_t)W * H * 3, sizeof(double));
+    double *den = (double *)calloc((size_t)W * H, sizeof(double));
+    int *acc = (int *)calloc((size_t)W * H, sizeof(int));
+    for (int yP = -rad; yP < H; yP++)
+        for (int xP = -rad; xP < W + rad; xP++) {
+            const int ypc = clampi(yP, 0, H - 1), xpc = clampi(xP, 0, W - 1);
+            const int p_real = yP >= 0 && xP >= 0 && xP < W; /* yP < H by the loop */
+            const float *mP = rowf(a->mean_corr, ypc) + xpc * C, *dP = rowf(a->disc, ypc) + xpc * C;
+            const float *vP = rowf(a->value, ypc) + xpc * VC;
+            if (p_real) { /* centre tap, weight 1 (SD.cu:78, 250-254) */
+                for (int c = 0; c < VC; c++) num[((size_t)yP * W + xP) * 3 + c] += (double)vP[c];
+                den[(size_t)yP * W + xP] += 1.0;
+                acc[(size_t)yP * W + xP]++;
+            }
+            for (int dy = 0; dy <= rad; dy++)
+                for (int dx = (dy == 0 ? 1 : -rad); dx <= rad; dx++) {
+                    if (dy * dy + dx * dx > rad2) continue;
+                    const int yQ = yP + dy, xQ = xP + dx;
+                    const int q_real = yQ >= 0 && yQ < H && xQ >= 0 && xQ < W;
+                    const int to_p = p_real && dy <= rad - 1 && dx <= rad - 1; /* (dy, dx) in P's window [-r, r) */
+                    const int to_q = q_real && dx >= -(rad - 1);               /* (-dy, -dx) in Q's window */
+                    if (!to_p && !to_q) continue;
+                    const int yqc = clampi(yQ, 0, H - 1), xqc = clampi(xQ, 0, W - 1);
+                    if (!member_welch(C, mP, dP, rowf(a->mean_corr, yqc) + xqc * C, rowf(a->disc, yqc) + xqc * C)) continue;
+                    double d2 = 0;
+                    for (int g = 0; g < a->n_gbufs; g++) {
+                        const int gc = a->gbuf_channels[g];
+                        const float *gP = rowf(&a->gbufs[g], ypc) + xpc * gc, *gQ = rowf(&a->gbufs[g], yqc) + xqc * gc;
+                        double t = 0;
+                        for (int c = 0; c < gc; c++) {
+                            const double df = (double)gP[c] - (double)gQ[c];
+                            t = fma(df, df, t);
+                        }
+                        d2 = fma(t, (double)a->gbuf_dr_factors[g], d2);
+                    }
+                    const double w = exp(fma((double)(dy * dy + dx * dx), (double)a->ds_factor, d2));
+                    const float *vQ = rowf(a->value, yqc) + xqc * VC;
+                    if (to_p) {
+                        for (int c = 0; c < VC; c++) num[((size_t)yP * W + xP) * 3 + c] += w * (double)vQ[c];
+                        den[(size_t)yP * W + xP] += w;
+                        acc[(size_t)yP * W + xP]++;
+                    }
+                    if (to_q) {
+                        for (int c = 0; c < VC; c++) num[((size_t)yQ * W + xQ) * 3 + c] += w * (double)vP[c];
+                        den[(size_t)yQ * W + xQ] += w;
+                        acc[(size_t)yQ * W + xQ]++;
+                    }
+                }
+        }
+    for (int y = 0; y < H; y++) {
+        float *o = rowf(a->out, y);
+        for (int x = 0; x < W; x++) {
+            for (int c = 0; c < VC; c++) o[x * VC + c] = (float)(num[((size_t)y * W + x) * 3 + c] / den[(size_t)y * W + x]);
+            if (a->accepted) rowi(a->accepted, y)[x] = acc[(size_t)y * W + x];
+        }
+    }
+    free(num);
+    free(den);
+    free(acc);
 }

@@ -269,3 +269,25 @@ def test_accumulate_oracle_on_the_reference_renderers_real_samples():
         po.ref_accumulate(h, smp, transform=True)
         for k in PLANES:
             assert bits_equal(h[k], ref[k]), k
+
+
+@pytest.mark.parametrize("W,H,radius,vary", [(70, 41, 6, False), (33, 9, 12, True), (50, 30, 1, False)])
+def test_symmetric_pair_evaluation_prototype(W, H, radius, vary):
+    """evaluating every unordered pair of positions once (forward offsets, two validity masks for
+    the half-open window, virtual border positions for the replicated edge) gives the reference's filter up to the order
+    of summation -- image smaller than the radius, varying n, NaN statistics and the scalar configuration included."""
+    from util import small_buffers
+    b = small_buffers(W, H, n=24, seed=5, vary_n=vary)
+    b["m2"][3, 4] = np.nan        # a pixel whose membership tests all fail: passes through, contributes to nobody
+    gb, fac, dsf = [b["normal"], b["albedo"]], [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2], -0.5 / (0.5 * radius + 1) ** 2
+    mc, dc = po.prepass(b["n"], b["mean"], b["m2"], b["m3"])
+    ref, acc = po.filter(b["film"], gb, fac, radius, dsf, mean_corr=mc, disc=dc, precision="f64", want_accepted=True)
+    sym, acc2 = po.filter(b["film"], gb, fac, radius, dsf, mean_corr=mc, disc=dc, precision="sym64", want_accepted=True)
+    assert np.array_equal(acc, acc2)                       # the same taps, pixel by pixel
+    assert rel_mad(sym, ref) < 1e-7 and np.allclose(sym, ref, rtol=2e-6, atol=0)
+    # scalar statistics gating a scalar value (filter<float>)
+    s = {k: np.ascontiguousarray(b[k][..., 1]) for k in ("mean", "m2", "m3", "film")}
+    mc1, dc1 = po.prepass(b["n"], s["mean"], s["m2"], s["m3"])
+    r1 = po.filter(s["film"], gb, fac, radius, dsf, mean_corr=mc1, disc=dc1, precision="f64")
+    s1 = po.filter(s["film"], gb, fac, radius, dsf, mean_corr=mc1, disc=dc1, precision="sym64")
+    assert np.allclose(s1, r1, rtol=2e-6, atol=0)
