@@ -75,5 +75,11 @@ def test_oracle_is_not_reachable_from_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "smo_" not in txt, f
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        assert "smo_" not in open(os.path.join(ROOT, "include", f)).read()
+    for d in ("include", "integration"):
+        for f in os.listdir(os.path.join(ROOT, d)):
+            txt = open(os.path.join(ROOT, d, f)).read()
+            assert "smo_" not in txt and "liboracle" not in txt and "pyoracle" not in txt, (d, f)
+    # and the shared library itself links nothing of the oracle
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", os.path.join(pkg, "libstatmc_b200.so")], capture_output=True, text=True).stdout
+    assert "liboracle" not in needed and "statmc_ref" not in needed
