@@ -156,7 +156,8 @@ int smc_accumulate(smc_context *ctx, const smc_moments *state, const float *samp
  * dst <- dst (+) src of two independently accumulated moment sets (n, mean, M2, M3 and film mean/M2). */
 int smc_merge_moments(smc_context *ctx, const smc_moments *dst, const smc_moments *src);
 /* calculate_mean_vars_kernel (SD.cu:148-159) / cv::cuda::stat_denoiser::calculateMeanVars<T> (CIP.hpp:745-754):
- * out = m2 / (n (n-1)) per pixel.  (The shipped CPU loop EST.cpp:524-568 reads n once per row; not replicated.) */
+ * out = m2 / (n (n-1)) per pixel.  (The CPU loop the reference ships instead, EST.cpp:524-568, reads n once per row and
+ * scales RGB planes by the reciprocal -- OpenCV's Vec3f / float -- so it is up to 1 ulp away; not replicated.) */
 int smc_calculate_mean_vars(smc_context *ctx, int width, int height, int channels, smc_plane n, smc_plane m2,
                             smc_plane out);
 

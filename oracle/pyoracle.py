@@ -100,6 +100,20 @@ def calculate_mean_vars(n: np.ndarray, m2: np.ndarray, per_row_n_bug: bool = Fal
     return out
 
 
+def calculate_mean_vars_cpu_loop(n: np.ndarray, m2: np.ndarray) -> np.ndarray:
+    """Estimator::CalculateMeanVars as the reference SHIPS it -- the CPU loop of estimator.cpp:524-568, not the CUDA kernel
+    it comments out: n is read once per row (`float nPF = (float) *nP` outside the column loop), and for RGB planes
+    `Vec3f / float` is OpenCV's scale by the reciprocal (matx.hpp:1499-1502: a * (1.f / alpha)), i.e. up to 1 ulp away from
+    the division the CUDA kernel (stat_denoiser.cu:148-159) and smc_calculate_mean_vars perform."""
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    m2 = np.ascontiguousarray(m2, dtype=np.float32)
+    nf = n[:, :1].astype(np.float32)                         # per-row n
+    den = (nf - np.float32(1)) * nf
+    if m2.ndim == 3:
+        return (m2 * (np.float32(1) / den)[:, :, None]).astype(np.float32)
+    return (m2 / den).astype(np.float32)
+
+
 def prepass(n: np.ndarray, mean: np.ndarray, m2: np.ndarray, m3: np.ndarray, lut: np.ndarray | None = None):
     """-> (mean_corr, disc) float32, stat_denoiser.cu:162-206."""
     H, W = n.shape

@@ -19,7 +19,7 @@ Integrator "statpath"
   "integer maxdepth" [16] "bool expiterations" ["true"] "integer iterations" [{iterations}]
   "integer trackedbounces" [{trackedbounces}] "bool multichannelstats" ["{multichannelstats}"]
   "bool denoiseimage" ["{denoiseimage}"] "bool acrr" ["{acrr}"] "bool smis" ["{smis}"]
-  "bool calcstats" ["false"] "bool calcprodenstats" ["false"] "bool calcmoonstats" ["false"] "bool calcgbuffers" ["false"]
+  "bool calcstats" ["false"] "bool calcprodenstats" ["{calcprodenstats}"] "bool calcmoonstats" ["false"] "bool calcgbuffers" ["false"]
   "bool calcitstats" ["false"]
   "float filtersd" [{sd}] "integer filterradius" [{radius}]
   "string filterbuffers" ["albedo" "normal"] "float filterbuffersds" [0.02 0.1]
@@ -63,16 +63,17 @@ WorldEnd
 
 
 def write_scene(directory, width=96, height=64, radius=8, sd=4.0, iterations=3, trackedbounces=0, multichannelstats=True,
-                denoiseimage=True, acrr=False, smis=False):
+                denoiseimage=True, acrr=False, smis=False, calcprodenstats=False):
     """scenes/render-denoise.pbrt by default; acrr.pbrt = trackedbounces 5, multichannelstats / denoiseimage false, acrr true;
-    smis.pbrt = trackedbounces 6, multichannelstats / denoiseimage false, smis true."""
+    smis.pbrt = trackedbounces 6, multichannelstats / denoiseimage false, smis true; render-for-proden.pbrt = denoiseimage
+    false, calcprodenstats true."""
     stem = os.path.join(str(directory), "smc")
     path = os.path.join(str(directory), "scene.pbrt")
     b = lambda v: "true" if v else "false"
     with open(path, "w") as f:
         f.write(SCENE.format(width=width, height=height, radius=radius, sd=sd, iterations=iterations, stem=stem,
                              trackedbounces=trackedbounces, multichannelstats=b(multichannelstats),
-                             denoiseimage=b(denoiseimage), acrr=b(acrr), smis=b(smis)))
+                             denoiseimage=b(denoiseimage), acrr=b(acrr), smis=b(smis), calcprodenstats=b(calcprodenstats)))
     return path, stem
 
 

@@ -95,3 +95,24 @@ def test_reference_renderer_acrr_and_smis_configurations(tmp_path, mode):
             assert bits_equal(ref, pl["film_mean_f"]), (t, j)
             checked += 1
     assert checked == len(filtered) * nb
+
+
+@pytest.mark.skipif(not os.path.exists(ru.PBRT_CPU), reason="oracle/_ref/pbrt_ref_cpu not built (needs /root/reference)")
+def test_reference_mean_vars_cpu_loop_vs_the_cuda_kernel_semantics(tmp_path):
+    """scenes/render-for-proden.pbrt: the estimator-variance planes `film-mean-var` come from the CPU loop the reference ships
+    (estimator.cpp:524-568).  For RGB planes that loop multiplies by the reciprocal (OpenCV's Vec3f / float), the CUDA kernel
+    it replaced -- and smc_calculate_mean_vars, which follows the kernel -- divides: at most 1 ulp apart."""
+    from statmc_b200 import pfm
+    lut = str(tmp_path / "t005.f32")
+    po.t_table(0.005).tofile(lut)
+    scene, stem = ru.write_scene(tmp_path, width=80, height=48, denoiseimage=False, calcprodenstats=True)
+    p = ru.run_pbrt(ru.PBRT_CPU, scene, "--writeimages", env={"STATMC_T_LUT": lut})
+    assert "CUDA time [ns]: 0" in p.stdout                      # nothing to denoise: runCUDA stays false (statpath.cpp:406)
+    for t in (0, 1, 2):                                          # radiance, normal, albedo
+        n = pfm.read("%s-16-t%d-b0-n.pfm" % (stem, t), np.int32)
+        m2 = pfm.read("%s-16-t%d-b0-film-m2.pfm" % (stem, t))
+        var = pfm.read("%s-16-t%d-b0-film-mean-var.pfm" % (stem, t))
+        assert bits_equal(po.calculate_mean_vars_cpu_loop(n, m2), var), t
+        kernel = po.calculate_mean_vars(n, m2)                   # stat_denoiser.cu:148-159 semantics
+        ulp = np.spacing(np.abs(var))
+        assert np.all(np.abs(kernel - var) <= ulp) and float(np.mean(kernel != var)) > 0.05
