@@ -201,7 +201,10 @@ typedef struct smc_filter_desc {
      * set, the `radius` record rows above row 0 / below row height-1 are NOT replicated from the edge row by the
      * prepass; the caller fills them from the neighbouring rank via smc_denoiser_halo() before smc_denoiser_filter(). */
     int halo_top_external, halo_bottom_external;
-    int kernel; /* 0 = auto, 1 = force the generic (any-radius, any-config) kernel, 2 = force the streaming kernel */
+    int kernel; /* 0 = auto (symmetric kernel where it applies -- RGB statistics, Welch membership, radius >= 2 --, else the
+                 * one-sided streaming kernel, else generic), 1 = force the generic (any-radius, any-config) kernel,
+                 * 2 = force the one-sided streaming kernel, 3 = force the symmetric kernel.  The symmetric kernel evaluates every
+                 * unordered pair once; its accept/reject decisions are identical, its sums differ in summation order only */
 } smc_filter_desc;
 
 /* Builds the plan: validates, uploads descriptor tables, allocates the packed per-pixel record array

@@ -174,19 +174,27 @@ def filter(value: np.ndarray, gbufs, gbuf_dr_factors, radius: int, ds_factor: fl
     return (out, acc) if want_accepted else out
 
 
+def f32_factor(sd: float) -> float:
+    """-.5f / (sd * sd) in float32 arithmetic, as the reference forms dSFactor and the range factors (estimator.h:259,
+    estimator.cpp:16): -49.999996 for sd = 0.1, not -50."""
+    s = np.float32(sd)
+    return float(np.float32(-0.5) / (s * s))
+
+
 def denoise(bufs: dict, radius: int = 20, sd: float = 10.0, gbuf_names=("normal", "albedo"),
             gbuf_sds=(0.1, 0.02), precision: str = "f32", mode: int = 0, lut=None, want_aux: bool = False):
     """The whole reference chain on one RGB image with denoiseFilm = true (estimator.cpp:462-488): prepass on
     (n, mean, m2, m3), then filter `film` gated by those statistics."""
-    factors = [-0.5 / (s * s) for s in gbuf_sds]
+    factors = [f32_factor(s) for s in gbuf_sds]
     gb = [bufs[k] for k in gbuf_names]
+    ds = f32_factor(sd)
     if mode == 0:
         mc, dc = prepass(bufs["n"], bufs["mean"], bufs["m2"], bufs["m3"], lut)
-        out, acc = filter(bufs["film"], gb, factors, radius, -0.5 / (sd * sd), mean_corr=mc, disc=dc,
+        out, acc = filter(bufs["film"], gb, factors, radius, ds, mean_corr=mc, disc=dc,
                           precision=precision, want_accepted=True)
         res = {"film_f": out, "accepted": acc, "mean_corr": mc, "disc": dc}
     else:
-        out, acc = filter(bufs["film"], gb, factors, radius, -0.5 / (sd * sd), n=bufs["n"], mean=bufs["mean"],
+        out, acc = filter(bufs["film"], gb, factors, radius, ds, n=bufs["n"], mean=bufs["mean"],
                           m2=bufs["m2"], lut=lut, mode=1, precision=precision, want_accepted=True)
         res = {"film_f": out, "accepted": acc}
     return res if want_aux else res["film_f"]

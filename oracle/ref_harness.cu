@@ -146,6 +146,93 @@ int smr_calculate_mean_vars(int channels, int W, int H, smr_plane n, smr_plane m
     return e;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Self-contained timing of the reference path for bench.py --impl reference: allocation (cudaMallocPitch, what
+// GpuMat(rows, cols, type) does, gpu_mat.cu:112-123), copies (cudaMemcpy2DAsync, gpu_mat.cu:224-234) and the three
+// reference kernels, all with plain CUDA runtime calls on one stream -- nothing of libstatmc_b200 is involved.
+//   host planes: n (int32, W), mean/m2/m3/film/normal/albedo (float32, 3W), tightly packed rows
+//   kernel_ms:   CUDA events around `steps` x filter<float3> (johnson + discriminator + filter kernels), device-resident
+//   e2e_ms[0]:   Upload(); Denoise(); Download(); Synchronize() per step as Estimator does (statpath.cpp:406-418),
+//                from the host memory it was given (pageable cv::Mat memory in the reference)
+//   e2e_ms[1]:   the same with the host planes page-locked first (cudaHostRegister): separates the copy policy from the
+//                kernels' speed
+// Returns 0, or the first CUDA error.
+// ---------------------------------------------------------------------------------------------------------------
+int smr_bench_rgb(int W, int H, int radius, float ds_factor, const float *gbuf_dr_factors, const int *h_n,
+                  const float *h_mean, const float *h_m2, const float *h_m3, const float *h_film, const float *h_normal,
+                  const float *h_albedo, float *h_out, int steps, int warmup, double *kernel_ms, double *e2e_ms) {
+#define SMR_CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::fprintf(stderr, "[statmc ref] %s: %s\n", #x, cudaGetErrorString(e__)); return (int)e__; } } while (0)
+    ref::setup();
+    cudaStream_t s;
+    SMR_CK(cudaStreamCreate(&s));
+    const void *host[7] = {h_n, h_mean, h_m2, h_m3, h_film, h_normal, h_albedo};
+    const size_t px[7] = {4, 12, 12, 12, 12, 12, 12};
+    smr_plane d[7], d_mc, d_disc, d_dummy, d_out;
+    for (int i = 0; i < 7; i++) SMR_CK(cudaMallocPitch(&d[i].dev, &d[i].step, (size_t)W * px[i], H));
+    SMR_CK(cudaMallocPitch(&d_mc.dev, &d_mc.step, (size_t)W * 12, H));
+    SMR_CK(cudaMallocPitch(&d_disc.dev, &d_disc.step, (size_t)W * 12, H));
+    SMR_CK(cudaMallocPitch(&d_dummy.dev, &d_dummy.step, (size_t)W * 12, H));
+    SMR_CK(cudaMallocPitch(&d_out.dev, &d_out.step, (size_t)W * 12, H));
+    const smr_plane g[2] = {d[5], d[6]};
+    const unsigned char gch[2] = {3, 3};
+    smr_filter *f = smr_filter_create(3, 1, W, H, ds_factor, radius, 1, &d[0], &d[1], &d[2], &d[3], &d[4], d[4], g, gch,
+                                      gbuf_dr_factors, 2, &d_mc, &d_disc, &d_dummy, d_out);
+    auto upload = [&]() -> cudaError_t {
+        for (int i = 0; i < 7; i++) {
+            cudaError_t e = cudaMemcpy2DAsync(d[i].dev, d[i].step, host[i], (size_t)W * px[i], (size_t)W * px[i], H,
+                                              cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    auto download = [&]() { return cudaMemcpy2DAsync(h_out, (size_t)W * 12, d_out.dev, d_out.step, (size_t)W * 12, H, cudaMemcpyDeviceToHost, s); };
+    SMR_CK(upload());
+    SMR_CK(cudaStreamSynchronize(s));
+    cudaEvent_t e0, e1;
+    SMR_CK(cudaEventCreate(&e0));
+    SMR_CK(cudaEventCreate(&e1));
+    float ms = 0.f;
+    for (int i = 0; i < warmup; i++) SMR_CK((cudaError_t)smr_filter_run(f, s));
+    SMR_CK(cudaStreamSynchronize(s));
+    SMR_CK(cudaEventRecord(e0, s));
+    for (int i = 0; i < steps; i++) SMR_CK((cudaError_t)smr_filter_run(f, s));
+    SMR_CK(cudaEventRecord(e1, s));
+    SMR_CK(cudaStreamSynchronize(s));
+    SMR_CK(cudaEventElapsedTime(&ms, e0, e1));
+    *kernel_ms = (double)ms / steps;
+    for (int pinned = 0; pinned < 2; pinned++) {
+        if (pinned) {
+            for (int i = 0; i < 7; i++) SMR_CK(cudaHostRegister((void *)host[i], (size_t)W * px[i] * H, cudaHostRegisterDefault));
+            SMR_CK(cudaHostRegister(h_out, (size_t)W * 12 * H, cudaHostRegisterDefault));
+        }
+        auto e2e = [&]() -> cudaError_t {
+            cudaError_t e = upload();
+            if (e != cudaSuccess) return e;
+            if ((e = (cudaError_t)smr_filter_run(f, s)) != cudaSuccess) return e;
+            if ((e = download()) != cudaSuccess) return e;
+            return cudaStreamSynchronize(s);
+        };
+        for (int i = 0; i < (warmup < 2 ? warmup : 2); i++) SMR_CK(e2e());
+        SMR_CK(cudaEventRecord(e0, s));
+        for (int i = 0; i < steps; i++) SMR_CK(e2e());
+        SMR_CK(cudaEventRecord(e1, s));
+        SMR_CK(cudaStreamSynchronize(s));
+        SMR_CK(cudaEventElapsedTime(&ms, e0, e1));
+        e2e_ms[pinned] = (double)ms / steps;
+        if (pinned) {
+            for (int i = 0; i < 7; i++) cudaHostUnregister((void *)host[i]);
+            cudaHostUnregister(h_out);
+        }
+    }
+    smr_filter_destroy(f);
+    for (int i = 0; i < 7; i++) cudaFree(d[i].dev);
+    cudaFree(d_mc.dev); cudaFree(d_disc.dev); cudaFree(d_dummy.dev); cudaFree(d_out.dev);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    return 0;
+#undef SMR_CK
+}
+
 int smr_synchronize(cudaStream_t stream) {
     ref::synchronize(stream);
     return (int)cudaGetLastError();

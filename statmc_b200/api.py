@@ -357,6 +357,13 @@ class MomentState:
         return {k: getattr(self, k).download() for k in ("n", "mean", "m2", "m3", "film_mean", "film_m2")}
 
 
+def f32_factor(sd: float) -> float:
+    """-.5f / (sd * sd) in float32 arithmetic, as the reference forms dSFactor and the range factors
+    (estimator.h:259, estimator.cpp:16; include/statmc_b200.hpp does the same)."""
+    s = np.float32(sd)
+    return float(np.float32(-0.5) / (s * s))
+
+
 def denoise_host(ctx: Context, bufs: dict, *, radius: int = 20, sd: float = 10.0, normal_sd: float = 0.1,
                  albedo_sd: float = 0.02, gbuf_names=("normal", "albedo"), gbuf_sds=None, kernel: int = 0,
                  membership: int = capi.SMC_MEMBER_WELCH, want_aux: bool = False, row_begin: int = 0,
@@ -374,9 +381,9 @@ def denoise_host(ctx: Context, bufs: dict, *, radius: int = 20, sd: float = 10.0
     aux = {}
     if want_aux:
         aux = {"mean_corr": Buffer(ctx, H, W, 3), "disc": Buffer(ctx, H, W, 3), "accepted": Buffer(ctx, H, W, 1, np.int32)}
-    dn = Denoiser(ctx, channels=3, width=W, height=H, radius=radius, ds_factor=-0.5 / (sd * sd),
+    dn = Denoiser(ctx, channels=3, width=W, height=H, radius=radius, ds_factor=f32_factor(sd),
                   n=[dev["n"]], mean=[dev["mean"]], m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[dev["film"]],
-                  film=dev["film"], gbufs=g, gbuf_dr_factors=[-0.5 / (sds[k] ** 2) for k in gbuf_names],
+                  film=dev["film"], gbufs=g, gbuf_dr_factors=[f32_factor(sds[k]) for k in gbuf_names],
                   film_filtered_ptrs=[out], film_filtered=out, denoise_film=True, membership=membership,
                   mean_corr=[aux["mean_corr"]] if want_aux else None, disc=[aux["disc"]] if want_aux else None,
                   accepted=[aux["accepted"]] if want_aux else None, kernel=kernel, row_begin=row_begin,

@@ -31,8 +31,16 @@ struct smc_denoiser {
     SmcPtrStepSz film{}, film_filtered{};
     int padX = 0, rec_pitch = 0, rec_rows = 0, sw_stride = 0;
     size_t rec_image_stride = 0;
-    bool use_stream = false;
+    bool use_stream = false, use_sym = false;
     int py = 4;
+    // symmetric kernel: forward spatial table, scratch (partial mirror sums), forward-sum plane
+    float *d_sym_sw = nullptr;
+    int2 *d_sym_rowrange = nullptr;
+    float sym_sw_special = 0.f;
+    void *d_sym_zeros = nullptr;
+    float4 *d_sym_scratch = nullptr, *d_sym_fwd = nullptr;
+    int *d_sym_scratch_cnt = nullptr, *d_sym_fwd_cnt = nullptr;
+    size_t sym_scratch_elems = 0, sym_fwd_elems = 0;
     char kernel_name[64] = "generic";
     // host-pipelined run (smc_denoiser_run_host): host copy of the descriptor tables, copy streams, event pool
     std::vector<SmcPtrStepSz> h_tables;
@@ -97,10 +105,52 @@ static int build_spatial_table(smc_denoiser *d) {
     return SMC_OK;
 }
 
+// Forward spatial table of the symmetric kernel: rows dy = -MY .. r + MY, columns dx = -r - MX .. r + MX (+1 pad);
+// finite for the forward offsets that are taps of BOTH positions' windows: dy == 0 and dx in [1, r-1], or dy in [1, r-1] and
+// dS2 <= r^2.  (0, r) and (r, 0) -- taps of the lower / right position only -- are handled apart with sym_sw_special.
+static int build_sym_table(smc_denoiser *d) {
+    SmcFilterParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.radius = d->radius; p.W = d->W; p.row_begin = d->row_begin; p.row_end = d->row_end; p.ptr_count = d->ptr_count;
+    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = 3;
+    SmcSymParams g;
+    size_t smem = 0;
+    if (!smc_filter_sym_geometry(p, g, smem)) return SMC_OK;  // no symmetric variant for this plan
+    const int r = d->radius;
+    std::vector<float> sw((size_t)g.sw_rows * g.sw_stride, -INFINITY);
+    std::vector<int2> rr(g.sw_rows);
+    auto val = [&](int dS2) { return (float)((double)dS2 * (double)d->ds_factor * 1.4426950408889634); };
+    for (int tr = 0; tr < g.sw_rows; tr++) {
+        const int dy = tr - g.sw_my;
+        rr[tr] = make_int2(1 << 20, -(1 << 20));
+        if (dy < 0 || dy > r - 1) continue;
+        int lo = 1 << 20, hi = -(1 << 20);
+        for (int dx = (dy == 0 ? 1 : -r); dx <= r - 1; dx++) {
+            const int dS2 = dy * dy + dx * dx;
+            if (dS2 > r * r) continue;
+            sw[(size_t)tr * g.sw_stride + (dx + r + g.sw_mx)] = val(dS2);
+            lo = std::min(lo, dx);
+            hi = std::max(hi, dx);
+        }
+        if (lo <= hi) rr[tr] = make_int2(lo, hi + 1);  // +1: the lane's second column sees dx = j - 1
+    }
+    d->sym_sw_special = val(r * r);
+    SMC_CUDA(cudaMalloc(&d->d_sym_sw, sw.size() * sizeof(float)));
+    SMC_CUDA(cudaMalloc(&d->d_sym_rowrange, rr.size() * sizeof(int2)));
+    SMC_CUDA(cudaMemcpyAsync(d->d_sym_sw, sw.data(), sw.size() * sizeof(float), cudaMemcpyHostToDevice, d->ctx->stream));
+    SMC_CUDA(cudaMemcpyAsync(d->d_sym_rowrange, rr.data(), rr.size() * sizeof(int2), cudaMemcpyHostToDevice, d->ctx->stream));
+    const size_t zb = (size_t)g.macc_bytes;
+    SMC_CUDA(cudaMalloc(&d->d_sym_zeros, zb));
+    SMC_CUDA(cudaMemsetAsync(d->d_sym_zeros, 0, zb, d->ctx->stream));
+    SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));  // sources are stack/pageable
+    return SMC_OK;
+}
+
 static int alloc_records(smc_denoiser *d) {
     const int r = d->radius;
-    d->padX = ((r + 15) / 16) * 16;
-    if (d->padX == 0) d->padX = 16;
+    // >= 2r + 2 columns of replicated border: the symmetric kernel's virtual centres sit up to r columns outside the image and
+    // read r columns beyond themselves
+    d->padX = ((2 * r + 2 + 15) / 16) * 16;
     d->rec_pitch = ((d->W + 2 * d->padX + 15) / 16) * 16;
     d->rec_rows = d->H + 2 * r + 4;  // +4: rows only ever paired with out-of-range centre rows of the last tile
     d->rec_image_stride = (size_t)d->rec_rows * smc_rec_row_bytes(d->rec_pitch);
@@ -131,7 +181,17 @@ static int select_kernel(smc_denoiser *d) {
     if (d->kernel_pref == 2 && !ok)
         SMC_FAIL(SMC_ERR_UNSUPPORTED, "streaming kernel requested but not available for C=%d NG=%d r=%d", d->C, d->NG,
                  d->radius);
-    d->use_stream = ok && d->kernel_pref != 1;
+    // kernel choice: 0 = auto (symmetric where it applies, else one-sided streaming, else generic), 1 = generic,
+    // 2 = one-sided streaming, 3 = symmetric.  SMC_FILTER_KERNEL=stream|generic overrides `auto` for A/B runs.
+    const bool sym_ok = d->d_sym_sw != nullptr && smc_filter_sym_supported(p);
+    if (d->kernel_pref == 3 && !sym_ok)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "symmetric kernel requested but not available for C=%d mode=%d r=%d", d->C, d->mode,
+                 d->radius);
+    int pref = d->kernel_pref;
+    if (pref == 0)
+        if (const char *e = getenv("SMC_FILTER_KERNEL")) pref = !strcmp(e, "stream") ? 2 : !strcmp(e, "generic") ? 1 : 0;
+    d->use_sym = sym_ok && (pref == 0 || pref == 3);
+    d->use_stream = !d->use_sym && ok && pref != 1;
     // output rows per thread: 2 x 2 pixels per thread wastes less work at the rim of the window (x1.06 at r = 20,
     // x1.23 at r = 6, against x1.13 / x1.46 for 2 x 4) and leaves room for 3 CTAs per SM; measured faster at every
     // radius tried (profiles/r1_variants.md).  SMC_STREAM_PY=4 selects the 2 x 4 variant for experiments.
@@ -142,7 +202,7 @@ static int select_kernel(smc_denoiser *d) {
         SMC_CUDA(cudaMalloc(&d->d_trace, 4096 * 4 * sizeof(unsigned long long)));
         SMC_CUDA(cudaMemset(d->d_trace, 0, 4096 * 4 * sizeof(unsigned long long)));
     }
-    snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", d->use_stream ? "stream" : "generic");
+    snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", d->use_sym ? "sym" : d->use_stream ? "stream" : "generic");
     return SMC_OK;
 }
 
@@ -263,7 +323,8 @@ extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc
     d->film = SmcPtrStepSz{(unsigned char *)desc->film.dev, desc->film.step, d->W, d->H};
     d->film_filtered = SmcPtrStepSz{(unsigned char *)desc->film_filtered.dev, desc->film_filtered.step, d->W, d->H};
 
-    if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = select_kernel(d))) return fail(rc);
+    if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = build_sym_table(d)) || (rc = select_kernel(d)))
+        return fail(rc);
     *out = d;
     return SMC_OK;
 }
@@ -289,6 +350,13 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     cudaFree(d->d_gf);
     cudaFree(d->d_sw);
     cudaFree(d->d_rowrange);
+    cudaFree(d->d_sym_sw);
+    cudaFree(d->d_sym_rowrange);
+    cudaFree(d->d_sym_zeros);
+    cudaFree(d->d_sym_scratch);
+    cudaFree(d->d_sym_scratch_cnt);
+    cudaFree(d->d_sym_fwd);
+    cudaFree(d->d_sym_fwd_cnt);
     for (int w = 0; w < 2; w++)
         if (d->peer[w].ipc_base) cudaIpcCloseMemHandle(d->peer[w].ipc_base);
     cudaFree(d->d_rec);
@@ -336,6 +404,39 @@ static int filter_rows(smc_denoiser *d, int y0, int y1) {
     fill_filter_params(d, p);
     p.row_begin = y0;
     p.row_end = y1;
+    if (d->use_sym) {
+        SmcSymParams g;
+        size_t smem = 0;
+        if (!smc_filter_sym_geometry(p, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "symmetric filter: geometry not supported");
+        // scratch for the partial mirror sums and the forward sums of this row range (grown on demand; a launch over fewer
+        // rows needs less)
+        const size_t se = smc_filter_sym_scratch_elems(p, g), fe = (size_t)d->ptr_count * (y1 - y0) * d->W;
+        if (se > d->sym_scratch_elems || fe > d->sym_fwd_elems) {
+            SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));
+            cudaFree(d->d_sym_scratch); cudaFree(d->d_sym_scratch_cnt); cudaFree(d->d_sym_fwd); cudaFree(d->d_sym_fwd_cnt);
+            d->d_sym_scratch = d->d_sym_fwd = nullptr;
+            d->d_sym_scratch_cnt = d->d_sym_fwd_cnt = nullptr;
+            d->sym_scratch_elems = d->sym_fwd_elems = 0;
+            const size_t se2 = std::max(se, d->sym_scratch_elems), fe2 = std::max(fe, d->sym_fwd_elems);
+            if (cudaMalloc(&d->d_sym_scratch, se2 * sizeof(float4)) != cudaSuccess ||
+                cudaMalloc(&d->d_sym_fwd, fe2 * sizeof(float4)) != cudaSuccess ||
+                (d->t_acc && (cudaMalloc(&d->d_sym_scratch_cnt, se2 * sizeof(int)) != cudaSuccess ||
+                              cudaMalloc(&d->d_sym_fwd_cnt, fe2 * sizeof(int)) != cudaSuccess))) {
+                cudaGetLastError();
+                SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu MB of symmetric-filter scratch) failed",
+                         (se2 * 16 + fe2 * 16) >> 20);
+            }
+            d->sym_scratch_elems = se2;
+            d->sym_fwd_elems = fe2;
+        }
+        g.sw = d->d_sym_sw; g.rowrange = d->d_sym_rowrange; g.sw_special = d->sym_sw_special;
+        g.scratch = d->d_sym_scratch; g.scratch_cnt = d->d_sym_scratch_cnt; g.fwd = d->d_sym_fwd; g.fwd_cnt = d->d_sym_fwd_cnt;
+        g.zeros = d->d_sym_zeros; g.unit_counter = d->d_tile_counter;
+        const char *nm = nullptr;
+        const int rc = smc_launch_filter_sym(d->ctx, p, g, smem, &nm);
+        if (nm) snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", nm);
+        return rc;
+    }
     if (d->use_stream) {
         const char *nm = nullptr;
         const int rc = smc_launch_filter_stream(d->ctx, p, d->d_rowrange, d->py, &nm);
@@ -767,7 +868,8 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
             cudaMemcpy(d->d_gch, gch.data(), n_gbufs, cudaMemcpyHostToDevice);
             cudaMemcpy(d->d_gf, gf.data(), sizeof(float) * n_gbufs, cudaMemcpyHostToDevice);
         }
-        if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = select_kernel(d))) {
+        if ((rc = alloc_records(d)) || (rc = build_spatial_table(d)) || (rc = build_sym_table(d)) ||
+            (rc = select_kernel(d))) {
             smc_denoiser_destroy(d);
             return rc;
         }

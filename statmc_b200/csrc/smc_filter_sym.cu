@@ -1,0 +1,617 @@
+// smc_filter_sym.cu -- the B200 filter kernel, symmetric form: every unordered pair of positions is evaluated ONCE.
+//
+// The reference (filter_kernel<float3>, stat_denoiser.cu:276-345) visits, for every pixel C, every tap I of the window and
+// evaluates the membership test (:81-88) and the cross-bilateral weight (:90-112, :261).  Both are symmetric in (C, I):
+//   disc_C + disc_I <= 2 mc_C mc_I        and        exp(dS2 * dSFactor + sum_g drFactor_g |g_C - g_I|^2),
+// so the pair (P, Q = P + (dy, dx)) with a FORWARD offset -- dy == 0 and dx in [1, r], or dy in [1, r] -- is evaluated once and
+// booked twice: w * V(Q) to P's sums and w * V(P) to Q's.  The window is half-open ([-r, r) in both axes, :247-248) and cut to
+// the disc dS2 <= r^2 (:36); of all forward offsets in the disc only (0, r) and (r, 0) are not taps of P itself (their mirror
+// images (0, -r), (-r, 0) are taps of Q), so those two are booked to Q only.  Replicated borders (BrdReplicate, :30-37) become
+// VIRTUAL centres: P ranges over the image extended by r on the left, right and top; a virtual position carries the clamped
+// pixel's record (the prepass has materialised them in the padded record array) and receives nothing.
+//
+// Work decomposition (one CTA per SM, every WARP an independent worker):
+//   tile  = 64 x 2 centre positions: two columns x two rows per lane, centre statistics, values and forward sums in registers;
+//           the tile streams the r + 2 record rows y0 .. y0 + r + 1 through a two-slot shared-memory ring filled by 1-D TMA bulk
+//           copies (as smc_filter_stream.cu), one row ahead;
+//   mirror sums of a streamed row live in a shared-memory row buffer (x, y, z, den per record), read-modify-written by the
+//           lane that evaluates the pair (lanes of one instruction touch distinct records; the even / odd records of a row sit
+//           in separate arrays so that the LDS.128 / STS.128 of a warp are conflict-free).  The buffer of a row is LOADED by TMA
+//           together with the row's records (previous partial sums of the same row, or zeros on first touch) and STORED by TMA
+//           when the row is done, into a scratch array private to the work unit: no atomics, a fixed order of summation;
+//   unit  = a run of vertically adjacent tiles of one 64-column strip, processed top to bottom by one warp (units come off a
+//           global atomic counter).  Only rows at unit seams and strip seams end up with more than one partial sum;
+//   gather kernel: out(y, x) = (forward sums + the <= ~6 partial mirror sums that cover the pixel) / den.
+// Per unordered pair: membership 7 + weight 9 + four packed FFMA2 (two sums each way) instructions, against 2 x (7 + 9 + 4) for
+// the one-sided kernels.  Results differ from the one-sided kernels only in the ORDER of summation (accept / reject decisions
+// are bit-identical: same operands, same roundings).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "smc_filter_math.cuh"
+#include "smc_internal.h"
+
+namespace {
+
+constexpr int kTW = 64;        // centre columns per tile
+#ifndef SMC_SYM_WARPS
+#define SMC_SYM_WARPS 10       // warps per CTA the register allocation is bounded for (A/B knob)
+#endif
+constexpr int kSymMaxWarps = SMC_SYM_WARPS;
+constexpr int kSymThreads = kSymMaxWarps * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ SmcRec lds_rec(const unsigned char *p) {
+    SmcRec r;
+    r.c0 = *(const float4 *)(p);
+    r.c1 = *(const float4 *)(p + 16);
+    r.c2 = *(const float4 *)(p + 32);
+    r.c3 = *(const float4 *)(p + 48);
+    return r;
+}
+__device__ __forceinline__ SmcRec ldg_rec(const unsigned char *row, int pcol) {
+    const unsigned char *p = row + smc_rec_offset(pcol);
+    SmcRec r;
+    r.c0 = __ldg((const float4 *)(p));
+    r.c1 = __ldg((const float4 *)(p + 16));
+    r.c2 = __ldg((const float4 *)(p + 32));
+    r.c3 = __ldg((const float4 *)(p + 48));
+    return r;
+}
+
+// What a lane keeps about one centre position: the test / weight operands (SmcCentre), its value for the mirror
+// bookings, and its own (forward) sums.
+template <int C, int NG>
+struct SymCentre {
+    SmcCentre<C, NG> c;
+    float2 v01, v2o;   // (V.x, V.y), (V.z, 1)
+    float2 n01, n2d;   // forward sums: (num.x, num.y), (num.z, den)
+    int cnt;
+};
+
+// mirror sums of one record, as they sit in the row buffer
+struct Mir {
+    float2 m01, m2d;
+    int cnt;
+};
+
+// Orders the warp's shared-memory accesses for the compiler only.  The lanes of a warp run the row loop converged (its trip
+// counts and branches are warp-uniform; the warp is re-converged with __syncwarp() after the barrier wait), and a warp's
+// LDS / STS execute in program order, so lane l's read of the sums lane l + 1 wrote two steps earlier needs no instruction --
+// only that the compiler does not hoist the read above the write.  -DSMC_SYM_SYNCWARP=1 uses __syncwarp() instead.
+#ifndef SMC_SYM_SYNCWARP
+#define SMC_SYM_SYNCWARP 0
+#endif
+__device__ __forceinline__ void sym_order() {
+#if SMC_SYM_SYNCWARP
+    __syncwarp();
+#else
+    asm volatile("" ::: "memory");
+#endif
+}
+
+// 2^(sw - a), a = sum_k (g'_I,k - g'_C,k)^2, with the table holding (-sw, 0) so that the first squared difference is an FMA
+// onto it (one instruction fewer than smc_weight(); -sw = +inf outside the disc -> weight 0)
+template <int NG>
+__device__ __forceinline__ float sym_weight(const SmcCentre<3, NG> &c, const SmcRec &r, float2 nsw) {
+    float a;
+    if (NG >= 2) {
+        float2 e = smc_add2(make_float2(r.c2.z, r.c2.w), c.g[0]);
+        float2 acc = smc_fma2(e, e, nsw);
+        if (NG >= 4) {
+            e = smc_add2(make_float2(r.c3.x, r.c3.y), c.g[1]);
+            acc = smc_fma2(e, e, acc);
+        }
+        if (NG >= 6) {
+            e = smc_add2(make_float2(r.c3.z, r.c3.w), c.g[2]);
+            acc = smc_fma2(e, e, acc);
+        }
+        a = __fadd_rn(acc.x, acc.y);
+    } else {
+        a = nsw.x;
+    }
+    if (NG & 1) {
+        const float e = __fadd_rn(smc_rec_odd_g<NG>(r), c.go);
+        a = __fmaf_rn(e, e, a);
+    }
+    return smc_ex2(-a);
+}
+
+// One pair evaluation, booked both ways (forward to the centre, mirror to the record).  A rejected pair takes part with
+// weight 0 (one select) instead of predicating the four accumulations.
+template <int NG, bool COUNT>
+__device__ __forceinline__ void pair_sym(SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+    const bool ok = smc_member<3, NG, 0>(s.c, r);
+    const float w = ok ? sym_weight<NG>(s.c, r, nsw) : 0.f;
+    const float2 ww = make_float2(w, w);  // folded by ptxas into the scalar-broadcast operand form of FFMA2
+    s.n01 = smc_fma2(ww, make_float2(r.c2.x, r.c2.y), s.n01);
+    if (NG <= 6) {
+        s.n2d = smc_fma2(ww, make_float2(r.c1.z, r.c1.w), s.n2d);  // record slot 7 == 1.0f: den += w * 1
+        m.m2d = smc_fma2(ww, s.v2o, m.m2d);
+    } else {
+        s.n2d.x = __fmaf_rn(w, r.c1.z, s.n2d.x);
+        s.n2d.y = __fadd_rn(s.n2d.y, w);
+        m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+        m.m2d.y = __fadd_rn(m.m2d.y, w);
+    }
+    m.m01 = smc_fma2(ww, s.v01, m.m01);
+    if (COUNT) {
+        // a tap outside the disc has -sw = +inf -> w = 0: it adds nothing, but must not be counted
+        const int one = (ok && nsw.x != INFINITY) ? 1 : 0;
+        s.cnt += one;
+        m.cnt += one;
+    }
+}
+
+// The two forward offsets that are taps of the record's window only: booked to the record.
+template <int NG, bool COUNT>
+__device__ __forceinline__ void pair_mirror_only(const SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+    const bool ok = smc_member<3, NG, 0>(s.c, r);
+    const float w = ok ? sym_weight<NG>(s.c, r, nsw) : 0.f;
+    const float2 ww = make_float2(w, w);
+    m.m01 = smc_fma2(ww, s.v01, m.m01);
+    if (NG <= 6) {
+        m.m2d = smc_fma2(ww, s.v2o, m.m2d);
+    } else {
+        m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+        m.m2d.y = __fadd_rn(m.m2d.y, w);
+    }
+    if (COUNT) m.cnt += ok ? 1 : 0;
+}
+
+struct SymTile {
+    int z, sx, uy, k, nt;       // image, strip, unit row, tile within the unit, tiles of the unit
+    int x0, y0, i0, nrt;        // first centre column / row, first streamed row index, streamed rows
+    const unsigned char *src0;  // record segment of streamed row i0
+    uint32_t bytes;             // bytes per record segment
+    size_t scr0;                // float4 index of the scratch row of the unit's first row (row y = yfirst)
+    int yfirst;
+};
+
+__device__ __forceinline__ int sym_unit_t0(const SmcSymParams &g, int uy) {
+    return uy < g.n_big ? uy * g.u_big : g.n_big * g.u_big + (uy - g.n_big) * g.u_small;
+}
+__device__ __forceinline__ int sym_unit_srow0(const SmcSymParams &g, int uy, int r) {
+    return uy < g.n_big ? uy * (2 * g.u_big + r) : g.n_big * (2 * g.u_big + r) + (uy - g.n_big) * (2 * g.u_small + r);
+}
+__device__ __forceinline__ int sym_trow_unit(const SmcSymParams &g, int t) {
+    const int tb = g.n_big * g.u_big;
+    return t < tb ? t / g.u_big : g.n_big + (t - tb) / g.u_small;
+}
+
+__device__ __forceinline__ void sym_tile_place(SymTile &t, const SmcFilterParams &p, const SmcSymParams &g) {
+    const int r = p.radius;
+    const int t0 = sym_unit_t0(g, t.uy);
+    t.x0 = g.xorg + t.sx * kTW;
+    t.y0 = g.ystart + 2 * (t0 + t.k);
+    t.i0 = max(0, p.row_begin - t.y0);
+    t.nrt = r + 2 - t.i0;
+    const int seg_start = (t.x0 + p.padX - r) & ~1;
+    const int nrec = min(g.seg_rec, p.rec_pitch - seg_start);  // even
+    t.src0 = p.rec + (size_t)t.z * p.rec_image_stride + (size_t)(t.y0 + t.i0 + r) * smc_rec_row_bytes(p.rec_pitch) +
+             smc_rec_offset(seg_start);
+    t.bytes = (uint32_t)(nrec / 2) * SMC_LINE_BYTES;
+    t.yfirst = g.ystart + 2 * t0;
+    t.scr0 = ((size_t)(t.z * g.n_strips + t.sx) * g.scratch_rows + sym_unit_srow0(g, t.uy, r)) * (size_t)g.seg_rec;
+}
+
+__device__ __forceinline__ void sym_unit_start(SymTile &t, int u, const SmcFilterParams &p, const SmcSymParams &g) {
+    t.sx = u % g.n_strips;
+    const int q = u / g.n_strips;
+    t.uy = q % g.n_units_y;
+    t.z = q / g.n_units_y;
+    t.k = 0;
+    const int t0 = sym_unit_t0(g, t.uy);
+    t.nt = min(t.uy < g.n_big ? g.u_big : g.u_small, g.n_trows - t0);
+    sym_tile_place(t, p, g);
+}
+
+// One record row (already in the warp's ring slot, its mirror buffer loaded) against the warp's 2 x 2 centres per lane.
+template <int NG, bool COUNT>
+__device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<3, NG> (&cen)[2][2],
+                                        const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,
+                                        int *mcnt, int i, int base_idx) {
+    const int r = p.radius;
+    const int half = g.seg_rec >> 1;
+    // table row of centre row ky: dy = i - ky  ->  row index i - ky + margin
+    const int2 rr0 = rowrange[i + g.sw_my], rr1 = rowrange[i - 1 + g.sw_my];
+    const int lo = min(rr0.x, rr1.x), hi = max(rr0.y, rr1.y);
+    if (lo <= hi) {
+        const float2 *swp0 = sw + (i + g.sw_my) * g.sw_stride + (r + g.sw_mx) + lo;  // centre row ky = 0: dy = i
+        const float2 *swp1 = swp0 - g.sw_stride;                                     // centre row ky = 1: dy = i - 1
+        float2 sw_prev0 = swp0[-1], sw_prev1 = swp1[-1];
+        const int first = base_idx + lo;
+        const unsigned char *rp = slot + smc_rec_offset(first);
+        const int par = first & 1;
+        const int d0 = par ? SMC_LINE_BYTES - SMC_REC_BYTES : SMC_REC_BYTES;
+        float4 *mp0 = macc + par * half + (first >> 1);               // sums of record `first`, then first + 2, ...
+        float4 *mp1 = macc + (par ^ 1) * half + ((first + 1) >> 1);   // sums of record first + 1, first + 3, ...
+        int *cp0 = mcnt + par * half + (first >> 1), *cp1 = mcnt + (par ^ 1) * half + ((first + 1) >> 1);
+        SmcRec cur = lds_rec(rp);
+        // (centre kx = 0 sees the record at dx = j, centre kx = 1 at dx = j - 1: the table value of the previous step)
+        auto step = [&](const SmcRec &rec, float2 s0, float2 s1, float2 q0, float2 q1, float4 *mp, int *cp) {
+            sym_order();
+            const float4 mv = *mp;
+            Mir m;
+            m.m01 = make_float2(mv.x, mv.y);
+            m.m2d = make_float2(mv.z, mv.w);
+            m.cnt = COUNT ? *cp : 0;
+            pair_sym<NG, COUNT>(cen[0][0], rec, s0, m);
+            pair_sym<NG, COUNT>(cen[0][1], rec, q0, m);
+            pair_sym<NG, COUNT>(cen[1][0], rec, s1, m);
+            pair_sym<NG, COUNT>(cen[1][1], rec, q1, m);
+            *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
+            if (COUNT) *cp = m.cnt;
+            sym_order();
+        };
+        int j = lo;
+        for (; j + 1 <= hi; j += 2) {
+            const SmcRec nxt = lds_rec(rp + d0);
+            const float2 a0 = swp0[0], a1 = swp1[0], b0 = swp0[1], b1 = swp1[1];
+            step(cur, a0, a1, sw_prev0, sw_prev1, mp0, cp0);
+            rp += SMC_LINE_BYTES;
+            cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
+            step(nxt, b0, b1, a0, a1, mp1, cp1);
+            sw_prev0 = b0;
+            sw_prev1 = b1;
+            swp0 += 2; swp1 += 2;
+            mp0++; mp1++; cp0++; cp1++;
+        }
+        if (j <= hi) step(cur, swp0[0], swp1[0], sw_prev0, sw_prev1, mp0, cp0);
+    }
+    // the two offsets booked to the record only: (0, r) in the centre's own row, (r, 0) r rows below
+    auto special = [&](const SymCentre<3, NG> &s0, const SymCentre<3, NG> &s1, int dxs) {
+        const float2 nsw = make_float2(-g.sw_special, 0.f);
+#pragma unroll
+        for (int kx = 0; kx < 2; kx++) {
+            const int idx = base_idx + kx + dxs;
+            const SmcRec rec = lds_rec(slot + smc_rec_offset(idx));
+            float4 *mp = macc + (idx & 1) * half + (idx >> 1);
+            int *cp = mcnt + (idx & 1) * half + (idx >> 1);
+            __syncwarp();
+            const float4 mv = *mp;
+            Mir m;
+            m.m01 = make_float2(mv.x, mv.y);
+            m.m2d = make_float2(mv.z, mv.w);
+            m.cnt = COUNT ? *cp : 0;
+            pair_mirror_only<NG, COUNT>(kx ? s1 : s0, rec, nsw, m);
+            *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
+            if (COUNT) *cp = m.cnt;
+        }
+    };
+    if (i == 0) special(cen[0][0], cen[0][1], r);
+    if (i == 1) special(cen[1][0], cen[1][1], r);
+    if (i == r) special(cen[0][0], cen[0][1], 0);
+    if (i == r + 1) special(cen[1][0], cen[1][1], 0);
+}
+
+template <int NG, bool COUNT>
+__global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFilterParams p, const SmcSymParams g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [per warp: 2 record slots | 3 mirror buffers (| 3 count buffers)] ... [sw table][rowrange][barriers: nwarps x 2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wbase = smem + (size_t)warp * g.warp_bytes;
+    unsigned char *ring = wbase;
+    float4 *macc0 = (float4 *)(wbase + 2 * (size_t)g.slot_bytes);
+    int *mcnt0 = (int *)(wbase + 2 * (size_t)g.slot_bytes + 3 * (size_t)g.macc_bytes);
+    float2 *sw = (float2 *)(smem + (size_t)g.nwarps * g.warp_bytes);  // (-sw, 0) per forward offset
+    int2 *rowrange = (int2 *)(sw + g.sw_rows * g.sw_stride);
+    uint64_t *full = (uint64_t *)(rowrange + g.sw_rows) + 2 * warp;
+
+    for (int i = threadIdx.x; i < g.sw_rows * g.sw_stride; i += blockDim.x) sw[i] = make_float2(-g.sw[i], 0.f);
+    for (int i = threadIdx.x; i < g.sw_rows; i += blockDim.x) rowrange[i] = g.rowrange[i];
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide synchronisation
+
+    const int r = p.radius;
+    const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
+    const int total_warps = (int)gridDim.x * g.nwarps;
+    const int rows_out = p.row_end - p.row_begin;
+    // warps that run side by side start on neighbouring strips of the same unit row: the record rows they share come out of L2
+    int u_cur = (int)blockIdx.x * g.nwarps + warp;
+    if (u_cur >= g.units_total) return;
+    SymTile ti;
+    sym_unit_start(ti, u_cur, p, g);
+    const uint32_t full0 = smem_u32(&full[0]);
+    const uint32_t ring0 = smem_u32(ring), maccs = smem_u32(macc0), mcnts = smem_u32(mcnt0);
+    const uint32_t macc_bytes = (uint32_t)g.macc_bytes, cnt_bytes = (uint32_t)g.seg_rec * 4u;
+
+    // lane 0: queue the loads of stream position q = (tile t, streamed row i): the record segment into ring slot q & 1 and the
+    // row's partial mirror sums (zeros on first touch) into mirror buffer q % 3, all completing on full[q & 1]
+    auto issue = [&](const SymTile &t, int i, uint32_t q) {
+        const uint32_t s = q & 1u, b = q % 3u;
+        const uint32_t bar = full0 + 8u * s;
+        const bool first = t.k == 0 || i >= r;  // rows r, r + 1 of a tile are new to the unit; everything is for its first tile
+        const uint32_t tx = t.bytes + macc_bytes + (COUNT ? cnt_bytes : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ring0 + s * (uint32_t)g.slot_bytes),
+                     "l"(t.src0 + (size_t)(i - t.i0) * row_bytes), "r"(t.bytes), "r"(bar)
+                     : "memory");
+        const size_t e = t.scr0 + (size_t)(t.y0 + i - t.yfirst) * g.seg_rec;
+        const void *msrc = first ? (const void *)g.zeros : (const void *)(g.scratch + e);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         maccs + b * macc_bytes),
+                     "l"(msrc), "r"(macc_bytes), "r"(bar)
+                     : "memory");
+        if (COUNT) {
+            const void *csrc = first ? (const void *)g.zeros : (const void *)(g.scratch_cnt + e);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             mcnts + b * cnt_bytes),
+                         "l"(csrc), "r"(cnt_bytes), "r"(bar)
+                         : "memory");
+        }
+    };
+    if (lane == 0) {
+        issue(ti, ti.i0, 0u);
+        issue(ti, ti.i0 + 1, 1u);  // every tile streams at least two rows
+    }
+
+    uint32_t pos = 0;  // rows consumed so far: ring slot = pos & 1, phase parity = (pos >> 1) & 1, mirror buffer = pos % 3
+    int nxt_raw = 0;   // lane 0: the unit after the current one
+    for (;;) {
+        // asked for when a unit starts (~1 us), first needed two rows before the unit's last tile ends
+        if (ti.k == 0 && lane == 0) nxt_raw = total_warps + atomicAdd(g.unit_counter, 1);
+        SymTile tn = ti;
+        bool have_next = false;
+
+        const unsigned char *img = p.rec + (size_t)ti.z * p.rec_image_stride;
+        const int xf = ti.x0 + 2 * lane;  // first of this lane's two centre columns
+        const int base_idx = xf + p.padX - ((ti.x0 + p.padX - r) & ~1);  // slot index of the record at dx = 0, column kx = 0
+
+        SymCentre<3, NG> cen[2][2];
+        bool real[2][2];
+#pragma unroll
+        for (int ky = 0; ky < 2; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+                const int yc = ti.y0 + ky, xc = xf + kx;
+                // virtual positions (replicated borders, rows of other bands) carry the padded array's record
+                const int pcol = min(xc + p.padX, p.rec_pitch - 1);
+                const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, pcol);
+                SymCentre<3, NG> &s = cen[ky][kx];
+                smc_make_centre<3, NG, 0>(rc, s.c);
+                s.v01 = make_float2(rc.c2.x, rc.c2.y);
+                // (V.z, 1): slot 7 of the record holds 1.0f when it is not the seventh G channel -- taken from the record so
+                // that the pair sits in adjacent registers as loaded (a literal 1.f would be rebuilt with moves at every use)
+                s.v2o = make_float2(rc.c1.z, NG <= 6 ? rc.c1.w : 1.f);
+                real[ky][kx] = yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W;
+                // the centre tap: weight 1 unconditionally (is_center, stat_denoiser.cu:78, :318-323)
+                s.n01 = real[ky][kx] ? s.v01 : make_float2(0.f, 0.f);
+                s.n2d = real[ky][kx] ? s.v2o : make_float2(0.f, 0.f);
+                s.cnt = real[ky][kx] ? 1 : 0;
+            }
+
+        for (int ii = 0; ii < ti.nrt; ii++, pos++) {
+            const int i = ti.i0 + ii;
+            const uint32_t s = pos & 1u, b = pos % 3u;
+            {
+                const uint32_t bar = full0 + 8u * s, parity = (pos >> 1) & 1u;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "SWAIT_LOOP:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra SDONE;\n"
+                    "bra SWAIT_LOOP;\n"
+                    "SDONE:\n"
+                    "}\n" ::"r"(bar),
+                    "r"(parity)
+                    : "memory");
+            }
+            __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
+            sym_row<NG, COUNT>(p, g, cen, rowrange, sw, ring + (size_t)s * g.slot_bytes,
+                               (float4 *)((unsigned char *)macc0 + (size_t)b * macc_bytes),
+                               (int *)((unsigned char *)mcnt0 + (size_t)b * cnt_bytes), i, base_idx);
+            // every lane has read the slot and written its mirror sums, which the async proxy (the bulk store) reads next
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (ii == ti.nrt - 2) {  // the next tile's first row goes into this slot
+                if (ti.k + 1 < ti.nt) {
+                    tn = ti;
+                    tn.k = ti.k + 1;
+                    sym_tile_place(tn, p, g);
+                    have_next = true;
+                } else {
+                    const int u_next = __shfl_sync(0xffffffffu, nxt_raw, 0);
+                    if (u_next < g.units_total) {
+                        sym_unit_start(tn, u_next, p, g);
+                        have_next = true;
+                    }
+                }
+            }
+            if (lane == 0) {
+                // store this row's mirror sums to the unit's scratch
+                const size_t e = ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.scratch + e),
+                             "r"(maccs + b * macc_bytes), "r"(macc_bytes)
+                             : "memory");
+                if (COUNT)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.scratch_cnt + e),
+                                 "r"(mcnts + b * cnt_bytes), "r"(cnt_bytes)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // queue stream position pos + 2.  Its mirror buffer was last stored from by position pos - 1: that store
+                // must have finished READING shared memory; and if its partial sums were written by an earlier tile of this
+                // unit, that store (r - 2 positions back for full tiles) must be COMPLETE before the load is issued.
+                const int i2 = ii + 2;
+                const bool more = i2 < ti.nrt || have_next;
+                if (more) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (r >= 6 && ti.i0 == 0 && tn.i0 == 0)
+                        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                    else
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    if (i2 < ti.nrt) issue(ti, ti.i0 + i2, pos + 2u);
+                    else issue(tn, tn.i0 + (i2 - ti.nrt), pos + 2u);
+                }
+            }
+        }
+
+        // forward sums of the tile's real centres (two adjacent pixels per lane and row: 32 contiguous bytes)
+#pragma unroll
+        for (int ky = 0; ky < 2; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++)
+                if (real[ky][kx]) {
+                    const SymCentre<3, NG> &s = cen[ky][kx];
+                    const size_t o = ((size_t)ti.z * rows_out + (ti.y0 + ky - p.row_begin)) * p.W + (xf + kx);
+                    g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.n2d.x, s.n2d.y);
+                    if (COUNT) g.fwd_cnt[o] = s.cnt;
+                }
+        if (!have_next) break;
+        ti = tn;
+    }
+    // the scratch is read by the gather kernel: every store of this warp must have landed
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// out(y, x) = (forward sums + every partial mirror sum that covers the pixel) / den   (stat_denoiser.cu:341-344)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p, const SmcSymParams g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = p.row_begin + blockIdx.y;
+    const int z = blockIdx.z;
+    if (x >= p.W) return;
+    const int r = p.radius, rows_out = p.row_end - p.row_begin;
+    const size_t o = ((size_t)z * rows_out + (y - p.row_begin)) * p.W + x;
+    float4 s = g.fwd[o];
+    int cnt = COUNT ? g.fwd_cnt[o] : 0;
+    // tiles whose centre rows y - r .. y stream row y; strips whose centres reach column x
+    const int tlo = (y - r - g.ystart) >> 1, thi = min(g.n_trows - 1, (y - g.ystart) >> 1);
+    const int ulo = sym_trow_unit(g, tlo), uhi = sym_trow_unit(g, thi);
+    const int a = x - r - (kTW - 1) - g.xorg;
+    const int sxlo = a <= 0 ? 0 : (a + kTW - 1) / kTW, sxhi = min(g.n_strips - 1, (x + r - g.xorg) / kTW);
+    for (int sx = sxlo; sx <= sxhi; sx++) {
+        const int idx = x + p.padX - ((g.xorg + sx * kTW + p.padX - r) & ~1);
+        const int e = (idx & 1) * (g.seg_rec >> 1) + (idx >> 1);
+        for (int uy = ulo; uy <= uhi; uy++) {
+            const int yrel = y - (g.ystart + 2 * sym_unit_t0(g, uy));
+            const size_t q = (((size_t)(z * g.n_strips + sx) * g.scratch_rows + sym_unit_srow0(g, uy, r) + yrel) * g.seg_rec) + e;
+            const float4 v = __ldg(g.scratch + q);
+            s.x = __fadd_rn(s.x, v.x);
+            s.y = __fadd_rn(s.y, v.y);
+            s.z = __fadd_rn(s.z, v.z);
+            s.w = __fadd_rn(s.w, v.w);
+            if (COUNT) cnt += __ldg(g.scratch_cnt + q);
+        }
+    }
+    const SmcPtrStepSz ob = (p.denoise_film && z == 0) ? p.film_filtered : p.out_ptrs[z];
+    float *op = (float *)(ob.data + (size_t)y * ob.step) + x * 3;
+    op[0] = __fdiv_rn(s.x, s.w);
+    op[1] = __fdiv_rn(s.y, s.w);
+    op[2] = __fdiv_rn(s.z, s.w);
+    if (COUNT && p.accepted && p.accepted[z].data) ((int *)(p.accepted[z].data + (size_t)y * p.accepted[z].step))[x] = cnt;
+}
+
+template <int NG>
+int launch_sym_ng(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, int grid) {
+    if (p.accepted != nullptr) {
+        auto k = filter_sym_kernel<NG, true>;
+        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
+    } else {
+        auto k = filter_sym_kernel<NG, false>;
+        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
+    }
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
+}
+
+}  // namespace
+
+// ---- host side: geometry -----------------------------------------------------------------------------------------------
+bool smc_filter_sym_supported(const SmcFilterParams &p) {
+    if (p.C != 3 || p.mode != SMC_MEMBER_WELCH) return false;  // the Moon test is not symmetric (stat_denoiser.cu:132-143)
+    if (p.radius < 2 || p.radius > SMC_MAX_RADIUS) return false;
+    if (p.NG < 0 || p.NG > 7) return false;
+    if ((p.padX & 1) || (p.rec_pitch & 1)) return false;
+    const int xorg = -(p.radius + (p.radius & 1));
+    if (xorg + p.padX - p.radius < 0) return false;  // the first strip's record segment starts inside the padded array
+    SmcSymParams g;
+    size_t smem = 0;
+    return smc_filter_sym_geometry(p, g, smem);
+}
+
+// fills everything of `g` that follows from the filter parameters (tables, scratch pointers and counters are the caller's)
+bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &smem) {
+    const int r = p.radius;
+    g.xorg = -(r + (r & 1));
+    g.n_strips = (p.W + r - g.xorg + kTW - 1) / kTW;
+    g.ystart = p.row_begin - r;
+    g.n_trows = (p.row_end - g.ystart + 1) / 2;
+    g.seg_rec = kTW + 2 * r + 4;
+    g.slot_bytes = (((g.seg_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
+    g.macc_bytes = g.seg_rec * 16;
+    const bool count = p.accepted != nullptr;
+    g.warp_bytes = 2 * g.slot_bytes + 3 * g.macc_bytes + (count ? 3 * g.seg_rec * 4 : 0);
+    g.warp_bytes = ((g.warp_bytes + 127) / 128) * 128;
+    g.sw_my = 2;
+    g.sw_mx = 2;
+    g.sw_rows = r + 1 + 2 * g.sw_my;
+    g.sw_stride = 2 * r + 1 + 2 * g.sw_mx;
+    const size_t tables = (size_t)g.sw_rows * g.sw_stride * 8 + (size_t)g.sw_rows * 8;
+    const size_t avail = 227 * 1024 - 1024;
+    if (tables + 256 >= avail) return false;
+    int nw = (int)((avail - tables - kSymMaxWarps * 16) / (size_t)g.warp_bytes);
+    if (const char *e = getenv("SMC_SYM_NWARPS")) nw = std::min(nw, std::max(1, atoi(e)));  // tuning knob
+    g.nwarps = std::min(nw, kSymMaxWarps);
+    if (g.nwarps < 1) return false;
+    smem = (size_t)g.nwarps * g.warp_bytes + tables + (size_t)g.nwarps * 16;
+    // units: runs of u_big tiles for the upper part of the rows, u_small tiles for the rest (the tail of the work queue)
+    int u_big = 8, u_small = 2, small_pct = 12;
+    if (const char *e = getenv("SMC_SYM_UNIT")) sscanf(e, "%d,%d,%d", &u_big, &u_small, &small_pct);  // tuning knob
+    u_big = std::max(1, u_big);
+    u_small = std::max(1, std::min(u_small, u_big));
+    g.u_big = u_big;
+    g.u_small = u_small;
+    const int small_rows = (int)((long long)g.n_trows * small_pct / 100);
+    g.n_big = (g.n_trows - small_rows) / u_big;
+    const int rest = g.n_trows - g.n_big * u_big;
+    const int n_small = (rest + u_small - 1) / u_small;
+    g.n_units_y = g.n_big + n_small;
+    g.scratch_rows = g.n_big * (2 * u_big + r) + n_small * (2 * u_small + r);
+    const long long total = (long long)g.n_units_y * g.n_strips * p.ptr_count;
+    if (total <= 0 || total > 0x3fffffffLL) return false;
+    g.units_total = (int)total;
+    return true;
+}
+
+size_t smc_filter_sym_scratch_elems(const SmcFilterParams &p, const SmcSymParams &g) {
+    return (size_t)p.ptr_count * g.n_strips * g.scratch_rows * g.seg_rec;
+}
+
+int smc_launch_filter_sym(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, const char **name) {
+    const int rows = p.row_end - p.row_begin;
+    if (rows <= 0) return SMC_OK;
+    static thread_local char nm[80];
+    snprintf(nm, sizeof(nm), "sym-warp<NG=%d,PY=2,welch,W=%d,U=%d/%d>", p.NG, g.nwarps, g.u_big, g.u_small);
+    if (name) *name = nm;
+    const int grid = (int)std::min<long long>((g.units_total + g.nwarps - 1) / g.nwarps, (long long)ctx->sm_count);
+    SMC_CUDA(cudaMemsetAsync(g.unit_counter, 0, sizeof(int), ctx->stream));
+    int rc;
+    switch (p.NG) {
+        case 0: rc = launch_sym_ng<0>(ctx, p, g, smem, grid); break;
+        case 1: rc = launch_sym_ng<1>(ctx, p, g, smem, grid); break;
+        case 2: rc = launch_sym_ng<2>(ctx, p, g, smem, grid); break;
+        case 3: rc = launch_sym_ng<3>(ctx, p, g, smem, grid); break;
+        case 4: rc = launch_sym_ng<4>(ctx, p, g, smem, grid); break;
+        case 5: rc = launch_sym_ng<5>(ctx, p, g, smem, grid); break;
+        case 6: rc = launch_sym_ng<6>(ctx, p, g, smem, grid); break;
+        default: rc = launch_sym_ng<7>(ctx, p, g, smem, grid); break;
+    }
+    if (rc) return rc;
+    const dim3 gb(128), gg((p.W + 127) / 128, rows, p.ptr_count);
+    if (p.accepted != nullptr) sym_gather_kernel<true><<<gg, gb, 0, ctx->stream>>>(p, g);
+    else sym_gather_kernel<false><<<gg, gb, 0, ctx->stream>>>(p, g);
+    SMC_CHECK_LAUNCH(ctx);
+    return SMC_OK;
+}

@@ -120,6 +120,30 @@ struct SmcFilterParams {
     unsigned long long *trace;     // debug (SMC_STREAM_TRACE): per CTA {start ns, end ns, smid, tiles}; normally null
 };
 
+// parameters of the symmetric filter kernel (smc_filter_sym.cu), passed by value next to SmcFilterParams
+struct SmcSymParams {
+    int xorg;          // first centre column of strip 0 (even, <= -radius): strips cover [xorg, W + radius)
+    int n_strips;
+    int ystart;        // first centre row = row_begin - radius
+    int n_trows;       // tile rows (two centre rows each) covering [ystart, row_end)
+    int n_units_y;     // units per strip: n_big runs of u_big tiles, then runs of u_small tiles (the tail of the work queue)
+    int n_big, u_big, u_small;
+    int units_total;   // n_units_y * n_strips * ptr_count
+    int scratch_rows;  // scratch rows per (image, strip): sum over units of (2 * tiles + radius)
+    int seg_rec;       // records per streamed row segment (even) = entries per scratch row
+    int slot_bytes, macc_bytes, warp_bytes, nwarps;
+    int sw_stride, sw_rows, sw_my, sw_mx;  // forward spatial table: rows dy = -sw_my .. radius + sw_my
+    float sw_special;  // table value of dS2 = radius^2: the offsets (0, r) and (r, 0), booked to the record only
+    const float *sw;
+    const int2 *rowrange;
+    float4 *scratch;   // [image][strip][scratch_rows][seg_rec]: partial mirror sums (x, y, z, den)
+    int *scratch_cnt;  // same indexing: partial accepted-tap counts (only with an `accepted` plane)
+    float4 *fwd;       // [image][row_end - row_begin][W]: forward sums
+    int *fwd_cnt;
+    const void *zeros; // >= macc_bytes zero bytes: what a row's mirror buffer is loaded from on first touch
+    int *unit_counter;
+};
+
 struct SmcPrepassParams {
     int W, H, C, ptr_count, radius, mode, denoise_film;
     int padX, rec_pitch;
@@ -156,5 +180,10 @@ int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const i
 // the width in pixels of the tile one worker owns
 int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count, int *tile_w);
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name);
+// symmetric kernel: every unordered pair evaluated once (RGB statistics, Welch membership, any radius 2..255, any NG)
+bool smc_filter_sym_supported(const SmcFilterParams &p);
+bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &smem);
+size_t smc_filter_sym_scratch_elems(const SmcFilterParams &p, const SmcSymParams &g);
+int smc_launch_filter_sym(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, const char **name);
 #define SMC_SW_MARGIN_Y 3
 #define SMC_SW_MARGIN_X 2

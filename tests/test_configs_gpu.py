@@ -99,19 +99,24 @@ def test_config3_4k_crops_and_kernel_agreement(ctx):
     W, H, r, sd = 3840, 2160, 20, 10.0
     b = synth.moment_buffers(W, H, n=64, config_id=3)
     ours = denoise_host(ctx, b, radius=r, sd=sd, want_aux=True)
-    assert "stream" in ours["kernel"] and np.isfinite(ours["film_f"]).all()
-    _crops_vs_oracle(b, ours, r, sd, [(0, 0, 48, 64), (H - 40, W - 72, 40, 72), (1000, 1900, 64, 64), (517, 3001, 33, 95)])
-    # the generic kernel over a row band of the same frame: bit-identical to the streaming kernel's rows
+    assert "sym" in ours["kernel"] and np.isfinite(ours["film_f"]).all()
+    crops = [(0, 0, 48, 64), (H - 40, W - 72, 40, 72), (1000, 1900, 64, 64), (517, 3001, 33, 95)]
+    _crops_vs_oracle(b, ours, r, sd, crops)
+    one = denoise_host(ctx, b, radius=r, sd=sd, kernel=2, want_aux=True)
+    assert "stream" in one["kernel"]
+    _crops_vs_oracle(b, one, r, sd, crops[:2])
+    assert np.array_equal(one["accepted"], ours["accepted"]) and rel_mad(ours["film_f"], one["film_f"]) <= 1e-6
+    # the generic kernel over a row band of the same frame: bit-identical to the one-sided streaming kernel's rows
     band = {k: np.ascontiguousarray(v[600:600 + 16 + 2 * r]) for k, v in b.items()}
     g = denoise_host(ctx, band, radius=r, sd=sd, kernel=1, row_begin=r, row_end=r + 16)["film_f"]
-    assert bits_equal(g[r:r + 16], ours["film_f"][600 + r:600 + r + 16])
+    assert bits_equal(g[r:r + 16], one["film_f"][600 + r:600 + r + 16])
 
 
 def test_config4_8k_width_large_radius(ctx):
     W, H, r, sd = 7680, 1080, 40, 20.0
     b = synth.moment_buffers(W, H, n=64, config_id=4, vary_n=True)
     ours = denoise_host(ctx, b, radius=r, sd=sd, want_aux=True)
-    assert "stream" in ours["kernel"] and np.isfinite(ours["film_f"][b["n"] >= 2]).all()
+    assert "sym" in ours["kernel"] and np.isfinite(ours["film_f"][b["n"] >= 2]).all()
     _crops_vs_oracle(b, ours, r, sd, [(0, W - 64, 32, 64), (H - 24, 0, 24, 48), (500, 4000, 40, 56)])
 
 

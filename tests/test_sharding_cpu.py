@@ -65,8 +65,8 @@ def _worker(rank, world, port, W, H, radius, sd, q):
     if rank < world - 1:
         parts.append(below.numpy())
     ext = np.concatenate(parts, axis=0)
-    f = [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2]
-    out = po.filter(ext[..., 6:9], [ext[..., 9:12], ext[..., 12:15]], f, radius, -0.5 / (sd * sd),
+    f = [po.f32_factor(0.1), po.f32_factor(0.02)]
+    out = po.filter(ext[..., 6:9], [ext[..., 9:12], ext[..., 12:15]], f, radius, po.f32_factor(sd),
                     mean_corr=ext[..., 0:3], disc=ext[..., 3:6], precision="f32")
     q.put((rank, out[row_begin:row_begin + (y1 - y0)]))
     dist.barrier()

@@ -1,0 +1,23 @@
+#!/bin/bash
+# scratch driver for one gpurun call: ./tools/gpu_session.sh <stage ...>; logs under gpurun_out/
+mkdir -p gpurun_out
+P='import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print("%7.1f Mpix/s step %.3f ms filter %.3f ms prepass %.3f ms  %s  parity=%s  e2e=%s" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline_prepass"]["kernel_ms"], d["config"]["kernel"], json.dumps(d.get("parity") and {k: d["parity"][k] for k in ("rel_mad","flips","ok","timed_plan_bit_identical")}), d.get("e2e") and round(d["e2e"]["value"],1)))'
+QB="python bench.py --no-cpu-baseline --no-accum --no-8k"
+for stage in "$@"; do
+  echo "=== $stage"
+  case $stage in
+    tests_denoiser) timeout 900 python -m pytest tests/test_denoiser_gpu.py -m gpu -x -q --timeout 300 2>&1 | tail -15 ;;
+    tests_all) timeout 2400 python -m pytest tests -m gpu -x -q --timeout 600 2>&1 | tail -15 ;;
+    bench_sym) timeout 600 $QB --no-e2e --steps 10 2>gpurun_out/bench_sym.err | tee gpurun_out/bench_sym.json | python -c "$P" || tail -5 gpurun_out/bench_sym.err ;;
+    bench_stream) SMC_FILTER_KERNEL=stream timeout 600 $QB --no-e2e --steps 10 2>gpurun_out/bench_stream.err | tee gpurun_out/bench_stream.json | python -c "$P" || tail -5 gpurun_out/bench_stream.err ;;
+    bench_e2e) timeout 600 $QB --steps 10 2>gpurun_out/bench_e2e.err | tee gpurun_out/bench_e2e.json | python -c "$P" || tail -5 gpurun_out/bench_e2e.err ;;
+    bench_full) timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_full.err | tee gpurun_out/bench_full.json | python -c "$P" || tail -5 gpurun_out/bench_full.err ;;
+    bench_ref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2>gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json | cut -c1-900 ;;
+    sweep_*) # sweep_<ENVVAR>=v1:v2:...   device-resident bench per value
+      kv=${stage#sweep_}; var=${kv%%=*}; vals=${kv#*=}
+      for v in ${vals//:/ }; do echo -n "[$var=$v] "; env $var=$v timeout 300 $QB --no-e2e --no-parity --steps 10 2>gpurun_out/sweep.err | python -c "$P" || tail -3 gpurun_out/sweep.err; done ;;
+    ncu_filter) timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_sym -s 3 -c 1 -f -o gpurun_out/prof_filter $QB --no-e2e --no-parity --steps 1 --warmup 3 > gpurun_out/ncu_filter.log 2>&1; tail -2 gpurun_out/ncu_filter.log ;;
+    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $QB --no-e2e --no-parity --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done

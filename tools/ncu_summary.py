@@ -18,9 +18,18 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct']
 
 
+def source_shas():
+    """sha of the kernel sources at capture time, in the form bench.py's ncu_traffic() checks"""
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    import bench
+    return ['# source_sha[%s]: %s' % (k, bench.source_sha(k)) for k in bench.KERNEL_SOURCES]
+
+
 def main():
     rep = sys.argv[1]
     extra = sys.argv[2:]
+    print('\n'.join(source_shas()))
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h, u = rows[0], rows[1]
