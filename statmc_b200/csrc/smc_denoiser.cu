@@ -34,7 +34,7 @@ struct smc_denoiser {
     bool use_stream = false, use_sym = false;
     int py = 4;
     // symmetric kernel: forward spatial table, scratch (partial mirror sums), forward-sum plane
-    float *d_sym_sw = nullptr;
+    float2 *d_sym_sw = nullptr;
     int2 *d_sym_rowrange = nullptr;
     float sym_sw_special = 0.f;
     void *d_sym_zeros = nullptr;
@@ -117,7 +117,8 @@ static int build_sym_table(smc_denoiser *d) {
     size_t smem = 0;
     if (!smc_filter_sym_geometry(p, g, smem)) return SMC_OK;  // no symmetric variant for this plan
     const int r = d->radius;
-    std::vector<float> sw((size_t)g.sw_rows * g.sw_stride, -INFINITY);
+    // entries are (-sw, 0): the kernel starts the sum of squared G-buffer differences from them with one packed FMA
+    std::vector<float2> sw((size_t)g.sw_rows * g.sw_stride, make_float2(INFINITY, 0.f));
     std::vector<int2> rr(g.sw_rows);
     auto val = [&](int dS2) { return (float)((double)dS2 * (double)d->ds_factor * 1.4426950408889634); };
     for (int tr = 0; tr < g.sw_rows; tr++) {
@@ -128,16 +129,16 @@ static int build_sym_table(smc_denoiser *d) {
         for (int dx = (dy == 0 ? 1 : -r); dx <= r - 1; dx++) {
             const int dS2 = dy * dy + dx * dx;
             if (dS2 > r * r) continue;
-            sw[(size_t)tr * g.sw_stride + (dx + r + g.sw_mx)] = val(dS2);
+            sw[(size_t)tr * g.sw_stride + (dx + r + g.sw_mx)] = make_float2(-val(dS2), 0.f);
             lo = std::min(lo, dx);
             hi = std::max(hi, dx);
         }
         if (lo <= hi) rr[tr] = make_int2(lo, hi + 1);  // +1: the lane's second column sees dx = j - 1
     }
     d->sym_sw_special = val(r * r);
-    SMC_CUDA(cudaMalloc(&d->d_sym_sw, sw.size() * sizeof(float)));
+    SMC_CUDA(cudaMalloc(&d->d_sym_sw, sw.size() * sizeof(float2)));
     SMC_CUDA(cudaMalloc(&d->d_sym_rowrange, rr.size() * sizeof(int2)));
-    SMC_CUDA(cudaMemcpyAsync(d->d_sym_sw, sw.data(), sw.size() * sizeof(float), cudaMemcpyHostToDevice, d->ctx->stream));
+    SMC_CUDA(cudaMemcpyAsync(d->d_sym_sw, sw.data(), sw.size() * sizeof(float2), cudaMemcpyHostToDevice, d->ctx->stream));
     SMC_CUDA(cudaMemcpyAsync(d->d_sym_rowrange, rr.data(), rr.size() * sizeof(int2), cudaMemcpyHostToDevice, d->ctx->stream));
     const size_t zb = (size_t)g.macc_bytes;
     SMC_CUDA(cudaMalloc(&d->d_sym_zeros, zb));

@@ -220,8 +220,9 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
     const int2 rr0 = rowrange[i + g.sw_my], rr1 = rowrange[i - 1 + g.sw_my];
     const int lo = min(rr0.x, rr1.x), hi = max(rr0.y, rr1.y);
     if (lo <= hi) {
-        const float2 *swp0 = sw + (i + g.sw_my) * g.sw_stride + (r + g.sw_mx) + lo;  // centre row ky = 0: dy = i
-        const float2 *swp1 = swp0 - g.sw_stride;                                     // centre row ky = 1: dy = i - 1
+        // `sw` holds the two table rows this streamed row needs: dy = i - 1 (centre row ky = 1), then dy = i (ky = 0)
+        const float2 *swp1 = sw + (r + g.sw_mx) + lo;
+        const float2 *swp0 = swp1 + g.sw_stride;
         float2 sw_prev0 = swp0[-1], sw_prev1 = swp1[-1];
         const int first = base_idx + lo;
         const unsigned char *rp = slot + smc_rec_offset(first);
@@ -232,35 +233,54 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
         int *cp0 = mcnt + par * half + (first >> 1), *cp1 = mcnt + (par ^ 1) * half + ((first + 1) >> 1);
         SmcRec cur = lds_rec(rp);
         // (centre kx = 0 sees the record at dx = j, centre kx = 1 at dx = j - 1: the table value of the previous step)
-        auto step = [&](const SmcRec &rec, float2 s0, float2 s1, float2 q0, float2 q1, float4 *mp, int *cp) {
-            sym_order();
+        auto load_m = [&](const float4 *mp, const int *cp) {
             const float4 mv = *mp;
             Mir m;
             m.m01 = make_float2(mv.x, mv.y);
             m.m2d = make_float2(mv.z, mv.w);
             m.cnt = COUNT ? *cp : 0;
-            pair_sym<NG, COUNT>(cen[0][0], rec, s0, m);
-            pair_sym<NG, COUNT>(cen[0][1], rec, q0, m);
-            pair_sym<NG, COUNT>(cen[1][0], rec, s1, m);
-            pair_sym<NG, COUNT>(cen[1][1], rec, q1, m);
+            return m;
+        };
+        auto store_m = [&](float4 *mp, int *cp, const Mir &m) {
             *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
             if (COUNT) *cp = m.cnt;
-            sym_order();
         };
         int j = lo;
         for (; j + 1 <= hi; j += 2) {
+            // two records per iteration (an even and an odd one: their sums sit in different arrays), eight independent pair
+            // evaluations for the scheduler to interleave
             const SmcRec nxt = lds_rec(rp + d0);
             const float2 a0 = swp0[0], a1 = swp1[0], b0 = swp0[1], b1 = swp1[1];
-            step(cur, a0, a1, sw_prev0, sw_prev1, mp0, cp0);
+            sym_order();
+            Mir ma = load_m(mp0, cp0), mb = load_m(mp1, cp1);
+            pair_sym<NG, COUNT>(cen[0][0], cur, a0, ma);
+            pair_sym<NG, COUNT>(cen[0][0], nxt, b0, mb);
+            pair_sym<NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
+            pair_sym<NG, COUNT>(cen[0][1], nxt, a0, mb);
+            pair_sym<NG, COUNT>(cen[1][0], cur, a1, ma);
+            pair_sym<NG, COUNT>(cen[1][0], nxt, b1, mb);
+            pair_sym<NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
+            pair_sym<NG, COUNT>(cen[1][1], nxt, a1, mb);
+            store_m(mp0, cp0, ma);
+            store_m(mp1, cp1, mb);
+            sym_order();
             rp += SMC_LINE_BYTES;
             cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
-            step(nxt, b0, b1, a0, a1, mp1, cp1);
             sw_prev0 = b0;
             sw_prev1 = b1;
             swp0 += 2; swp1 += 2;
             mp0++; mp1++; cp0++; cp1++;
         }
-        if (j <= hi) step(cur, swp0[0], swp1[0], sw_prev0, sw_prev1, mp0, cp0);
+        if (j <= hi) {
+            sym_order();
+            Mir ma = load_m(mp0, cp0);
+            pair_sym<NG, COUNT>(cen[0][0], cur, swp0[0], ma);
+            pair_sym<NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
+            pair_sym<NG, COUNT>(cen[1][0], cur, swp1[0], ma);
+            pair_sym<NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
+            store_m(mp0, cp0, ma);
+            sym_order();
+        }
     }
     // the two offsets booked to the record only: (0, r) in the centre's own row, (r, 0) r rows below
     auto special = [&](const SymCentre<3, NG> &s0, const SymCentre<3, NG> &s1, int dxs) {
@@ -291,17 +311,18 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
 template <int NG, bool COUNT>
 __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFilterParams p, const SmcSymParams g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [per warp: 2 record slots | 3 mirror buffers (| 3 count buffers)] ... [sw table][rowrange][barriers: nwarps x 2]
+    // layout: [per warp: 2 record slots | 2 x 2 spatial-table rows | 3 mirror buffers (| 3 count buffers)] ... [rowrange]
+    //         [barriers: nwarps x 2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wbase = smem + (size_t)warp * g.warp_bytes;
     unsigned char *ring = wbase;
-    float4 *macc0 = (float4 *)(wbase + 2 * (size_t)g.slot_bytes);
-    int *mcnt0 = (int *)(wbase + 2 * (size_t)g.slot_bytes + 3 * (size_t)g.macc_bytes);
-    float2 *sw = (float2 *)(smem + (size_t)g.nwarps * g.warp_bytes);  // (-sw, 0) per forward offset
-    int2 *rowrange = (int2 *)(sw + g.sw_rows * g.sw_stride);
+    const uint32_t sw_bytes = 2u * (uint32_t)g.sw_stride * 8u;  // two table rows of (-sw, 0) pairs
+    unsigned char *swb0 = wbase + 2 * (size_t)g.slot_bytes;
+    float4 *macc0 = (float4 *)(swb0 + 2 * (size_t)sw_bytes);
+    int *mcnt0 = (int *)((unsigned char *)macc0 + 3 * (size_t)g.macc_bytes);
+    int2 *rowrange = (int2 *)(smem + (size_t)g.nwarps * g.warp_bytes);
     uint64_t *full = (uint64_t *)(rowrange + g.sw_rows) + 2 * warp;
 
-    for (int i = threadIdx.x; i < g.sw_rows * g.sw_stride; i += blockDim.x) sw[i] = make_float2(-g.sw[i], 0.f);
     for (int i = threadIdx.x; i < g.sw_rows; i += blockDim.x) rowrange[i] = g.rowrange[i];
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
@@ -320,20 +341,25 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
     SymTile ti;
     sym_unit_start(ti, u_cur, p, g);
     const uint32_t full0 = smem_u32(&full[0]);
-    const uint32_t ring0 = smem_u32(ring), maccs = smem_u32(macc0), mcnts = smem_u32(mcnt0);
+    const uint32_t ring0 = smem_u32(ring), maccs = smem_u32(macc0), mcnts = smem_u32(mcnt0), sws = smem_u32(swb0);
     const uint32_t macc_bytes = (uint32_t)g.macc_bytes, cnt_bytes = (uint32_t)g.seg_rec * 4u;
 
-    // lane 0: queue the loads of stream position q = (tile t, streamed row i): the record segment into ring slot q & 1 and the
-    // row's partial mirror sums (zeros on first touch) into mirror buffer q % 3, all completing on full[q & 1]
+    // lane 0: queue the loads of stream position q = (tile t, streamed row i): the record segment and the two spatial-table
+    // rows (dy = i - 1, i) into ring slot q & 1 and the row's partial mirror sums (zeros on first touch) into mirror buffer
+    // q % 3, all completing on full[q & 1]
     auto issue = [&](const SymTile &t, int i, uint32_t q) {
         const uint32_t s = q & 1u, b = q % 3u;
         const uint32_t bar = full0 + 8u * s;
         const bool first = t.k == 0 || i >= r;  // rows r, r + 1 of a tile are new to the unit; everything is for its first tile
-        const uint32_t tx = t.bytes + macc_bytes + (COUNT ? cnt_bytes : 0u);
+        const uint32_t tx = t.bytes + sw_bytes + macc_bytes + (COUNT ? cnt_bytes : 0u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          ring0 + s * (uint32_t)g.slot_bytes),
                      "l"(t.src0 + (size_t)(i - t.i0) * row_bytes), "r"(t.bytes), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         sws + s * sw_bytes),
+                     "l"(g.sw + (size_t)(i - 1 + g.sw_my) * g.sw_stride), "r"(sw_bytes), "r"(bar)
                      : "memory");
         const size_t e = t.scr0 + (size_t)(t.y0 + i - t.yfirst) * g.seg_rec;
         const void *msrc = first ? (const void *)g.zeros : (const void *)(g.scratch + e);
@@ -407,7 +433,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                     : "memory");
             }
             __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
-            sym_row<NG, COUNT>(p, g, cen, rowrange, sw, ring + (size_t)s * g.slot_bytes,
+            sym_row<NG, COUNT>(p, g, cen, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
                                (float4 *)((unsigned char *)macc0 + (size_t)b * macc_bytes),
                                (int *)((unsigned char *)mcnt0 + (size_t)b * cnt_bytes), i, base_idx);
             // every lane has read the slot and written its mirror sums, which the async proxy (the bulk store) reads next
@@ -548,17 +574,17 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     g.n_strips = (p.W + r - g.xorg + kTW - 1) / kTW;
     g.ystart = p.row_begin - r;
     g.n_trows = (p.row_end - g.ystart + 1) / 2;
-    g.seg_rec = kTW + 2 * r + 4;
+    g.seg_rec = ((kTW + 2 * r + 4 + 3) / 4) * 4;  // multiple of 4: the count rows (4 B per record) move as 16-byte bulk copies
     g.slot_bytes = (((g.seg_rec / 2) * SMC_LINE_BYTES + 127) / 128) * 128;
     g.macc_bytes = g.seg_rec * 16;
     const bool count = p.accepted != nullptr;
-    g.warp_bytes = 2 * g.slot_bytes + 3 * g.macc_bytes + (count ? 3 * g.seg_rec * 4 : 0);
-    g.warp_bytes = ((g.warp_bytes + 127) / 128) * 128;
     g.sw_my = 2;
     g.sw_mx = 2;
     g.sw_rows = r + 1 + 2 * g.sw_my;
-    g.sw_stride = 2 * r + 1 + 2 * g.sw_mx;
-    const size_t tables = (size_t)g.sw_rows * g.sw_stride * 8 + (size_t)g.sw_rows * 8;
+    g.sw_stride = 2 * r + 2 + 2 * g.sw_mx;  // even: two table rows of 8-byte entries move as one 16-byte-aligned bulk copy
+    g.warp_bytes = 2 * g.slot_bytes + 2 * (2 * g.sw_stride * 8) + 3 * g.macc_bytes + (count ? 3 * g.seg_rec * 4 : 0);
+    g.warp_bytes = ((g.warp_bytes + 127) / 128) * 128;
+    const size_t tables = (size_t)g.sw_rows * 8;
     const size_t avail = 227 * 1024 - 1024;
     if (tables + 256 >= avail) return false;
     int nw = (int)((avail - tables - kSymMaxWarps * 16) / (size_t)g.warp_bytes);
@@ -567,7 +593,7 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     if (g.nwarps < 1) return false;
     smem = (size_t)g.nwarps * g.warp_bytes + tables + (size_t)g.nwarps * 16;
     // units: runs of u_big tiles for the upper part of the rows, u_small tiles for the rest (the tail of the work queue)
-    int u_big = 8, u_small = 2, small_pct = 12;
+    int u_big = 4, u_small = 2, small_pct = 12;
     if (const char *e = getenv("SMC_SYM_UNIT")) sscanf(e, "%d,%d,%d", &u_big, &u_small, &small_pct);  // tuning knob
     u_big = std::max(1, u_big);
     u_small = std::max(1, std::min(u_small, u_big));

@@ -134,7 +134,7 @@ struct SmcSymParams {
     int slot_bytes, macc_bytes, warp_bytes, nwarps;
     int sw_stride, sw_rows, sw_my, sw_mx;  // forward spatial table: rows dy = -sw_my .. radius + sw_my
     float sw_special;  // table value of dS2 = radius^2: the offsets (0, r) and (r, 0), booked to the record only
-    const float *sw;
+    const float2 *sw;  // (-sw, 0) per forward offset; +inf outside the disc
     const int2 *rowrange;
     float4 *scratch;   // [image][strip][scratch_rows][seg_rec]: partial mirror sums (x, y, z, den)
     int *scratch_cnt;  // same indexing: partial accepted-tap counts (only with an `accepted` plane)
