@@ -52,7 +52,10 @@ enum smc_membership {
  * SD.cu:214), ptr_count <= 65535 (grid.z, SD.cu:422). */
 #define SMC_MAX_DIM 65535
 #define SMC_MAX_RADIUS 255
-#define SMC_MAX_GBUF_CHANNELS 7 /* flattened G-buffer channels per image handled by this build (reference: unbounded) */
+#define SMC_MAX_GBUF_CHANNELS 23 /* flattened G-buffer channels handled by this build (reference: unbounded).  Up to 7 travel
+                                  * inside the packed per-pixel record (every kernel); channels 8..23 -- e.g. filterbuffers
+                                  * [materialid depth normal albedo] = 8 -- go through a side array and the generic kernel.
+                                  * G-buffers whose channel count is neither 1 nor 3 are ignored, as in dr2 (SD.cu:101-111) */
 #define SMC_T_LUT_ENTRIES 1024  /* SD.cu:43 */
 
 typedef struct smc_context smc_context;   /* one per (process, GPU): device, stream, t-quantile table */

@@ -13,6 +13,8 @@
 struct smc_denoiser {
     smc_context *ctx = nullptr;
     int C = 3, ptr_count = 1, W = 0, H = 0, radius = 0, denoise_film = 0, mode = 0, n_gbufs = 0, NG = 0;
+    int NGX = 0, gext_stride = 0;  // flattened G-buffer channels beyond the record's seven, and their side array
+    float *d_gext = nullptr;
     int row_begin = 0, row_end = 0;
     int skip_top = 0, skip_bottom = 0;
     int kernel_pref = 0;
@@ -49,6 +51,7 @@ struct smc_denoiser {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
     int *d_tile_counter = nullptr;
+    int *d_sync_counters = nullptr;  // [0] prepass, [1] filter: blocks retired (in-kernel halo protocol)
     // peer halos (multi-GPU, one process per GPU or several plans in one process): flags live behind the records in the
     // same allocation so that one IPC handle covers both.  flags: [0] ready_from_up [1] ready_from_down [2] free_from_up
     // [3] free_from_down, each holding the step number the neighbour has reached.
@@ -162,6 +165,15 @@ static int alloc_records(smc_denoiser *d) {
         SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu bytes of records) failed: %s", bytes, cudaGetErrorString(e));
     SMC_CUDA(cudaMemsetAsync(d->d_rec, 0, bytes, d->ctx->stream));
     d->d_flags = (int *)(d->d_rec + d->flags_offset);
+    if (d->NGX > 0) {
+        d->gext_stride = ((d->NGX + 3) / 4) * 4;
+        const size_t eb = (size_t)d->rec_rows * d->rec_pitch * d->gext_stride * sizeof(float);
+        if (cudaMalloc(&d->d_gext, eb) != cudaSuccess) {
+            cudaGetLastError();
+            SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu bytes of G-buffer extension) failed", eb);
+        }
+        SMC_CUDA(cudaMemsetAsync(d->d_gext, 0, eb, d->ctx->stream));
+    }
     return SMC_OK;
 }
 
@@ -172,6 +184,8 @@ static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p) {
     p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec;
     p.sw = d->d_sw; p.sw_stride = d->sw_stride; p.sw_margin_y = SMC_SW_MARGIN_Y; p.sw_margin_x = SMC_SW_MARGIN_X;
     p.out_ptrs = d->t_out; p.film_filtered = d->film_filtered; p.accepted = d->t_acc; p.trace = d->d_trace; p.tile_counter = d->d_tile_counter;
+    p.gext = d->d_gext; p.NGX = d->NGX; p.gext_stride = d->gext_stride;
+    std::memset(&p.halo, 0, sizeof(p.halo));
 }
 
 static int select_kernel(smc_denoiser *d) {
@@ -199,6 +213,10 @@ static int select_kernel(smc_denoiser *d) {
     d->py = 2;
     if (const char *e = getenv("SMC_STREAM_PY")) d->py = atoi(e) == 4 ? 4 : 2;
     if (!d->d_tile_counter) SMC_CUDA(cudaMalloc(&d->d_tile_counter, sizeof(int)));
+    if (!d->d_sync_counters) {
+        SMC_CUDA(cudaMalloc(&d->d_sync_counters, 2 * sizeof(int)));
+        SMC_CUDA(cudaMemsetAsync(d->d_sync_counters, 0, 2 * sizeof(int), d->ctx->stream));
+    }
     if (getenv("SMC_STREAM_TRACE") && !d->d_trace) {
         SMC_CUDA(cudaMalloc(&d->d_trace, 4096 * 4 * sizeof(unsigned long long)));
         SMC_CUDA(cudaMemset(d->d_trace, 0, 4096 * 4 * sizeof(unsigned long long)));
@@ -247,15 +265,17 @@ extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc
     for (int g = 0; g < desc->n_gbufs; g++) {
         if (!desc->gbufs || !desc->gbufs[g].dev || !desc->gbuf_channels || !desc->gbuf_dr_factors)
             SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d incomplete", g);
-        // the reference silently ignores channel counts other than 1 and 3 (stat_denoiser.cu:103-110); we reject them
-        if (desc->gbuf_channels[g] != 1 && desc->gbuf_channels[g] != 3)
-            SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d has %d channels (1 or 3 supported)", g, desc->gbuf_channels[g]);
+        // dr2 silently ignores buffers whose channel count is neither 1 nor 3 (stat_denoiser.cu:103-110): so do we
+        if (desc->gbuf_channels[g] != 1 && desc->gbuf_channels[g] != 3) continue;
         if (!(desc->gbuf_dr_factors[g] <= 0.f))
             SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d: drFactor %g must be <= 0 (-0.5/sd^2)", g, desc->gbuf_dr_factors[g]);
         ng += desc->gbuf_channels[g];
     }
     if (ng > SMC_MAX_GBUF_CHANNELS)
         SMC_FAIL(SMC_ERR_UNSUPPORTED, "%d flattened G-buffer channels; this build handles %d", ng, SMC_MAX_GBUF_CHANNELS);
+    if (ng > SMC_REC_GBUF_CHANNELS && (desc->halo_top_external || desc->halo_bottom_external))
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "more than %d G-buffer channels are not supported with external record halos",
+                 SMC_REC_GBUF_CHANNELS);
     int rb = desc->row_begin, re = desc->row_end;
     if (rb == 0 && re == 0) re = desc->height;
     if (rb < 0 || re > desc->height || rb > re) SMC_FAIL(SMC_ERR_INVALID, "bad row range [%d, %d)", rb, re);
@@ -265,7 +285,8 @@ extern "C" int smc_denoiser_create(smc_context *ctx, const smc_filter_desc *desc
     if (!d) SMC_FAIL(SMC_ERR_NOMEM, "out of host memory");
     d->ctx = ctx; d->C = desc->channels; d->ptr_count = pc; d->W = desc->width; d->H = desc->height;
     d->radius = desc->radius; d->denoise_film = desc->denoise_film ? 1 : 0; d->mode = desc->membership;
-    d->n_gbufs = desc->n_gbufs; d->NG = ng; d->row_begin = rb; d->row_end = re; d->ds_factor = desc->ds_factor;
+    d->n_gbufs = desc->n_gbufs; d->NG = std::min(ng, SMC_REC_GBUF_CHANNELS); d->NGX = ng - d->NG;
+    d->row_begin = rb; d->row_end = re; d->ds_factor = desc->ds_factor;
     d->skip_top = desc->halo_top_external ? 1 : 0; d->skip_bottom = desc->halo_bottom_external ? 1 : 0;
     d->kernel_pref = desc->kernel;
 
@@ -361,7 +382,9 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     for (int w = 0; w < 2; w++)
         if (d->peer[w].ipc_base) cudaIpcCloseMemHandle(d->peer[w].ipc_base);
     cudaFree(d->d_rec);
+    cudaFree(d->d_gext);
     cudaFree(d->d_tile_counter);
+    cudaFree(d->d_sync_counters);
     for (cudaEvent_t e : d->events) cudaEventDestroy(e);
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);
@@ -369,21 +392,25 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
 }
 
 // prepass over image rows [y0, y1); the replicated rows above row 0 / below row H-1 go with the first / last rows
-static int prepass_rows(smc_denoiser *d, int y0, int y1) {
+static int prepass_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo = nullptr) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
     SmcPrepassParams p;
+    std::memset(&p.halo, 0, sizeof(p.halo));
+    p.halo_blocks = 0;
     p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->ptr_count; p.radius = d->radius; p.mode = d->mode;
     p.denoise_film = d->denoise_film; p.padX = d->padX; p.rec_pitch = d->rec_pitch;
     p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec; p.skip_top = d->skip_top; p.skip_bottom = d->skip_bottom;
     p.pr_begin = y0 == 0 ? 0 : y0 + d->radius;
     p.pr_end = y1 == d->H ? d->H + 2 * d->radius : y1 + d->radius;
     p.n = d->t_n; p.mean = d->t_mean; p.m2 = d->t_m2; p.m3 = d->t_m3; p.film_ptrs = d->t_film; p.film = d->film;
-    p.gbufs = d->t_gbufs; p.NG = d->NG;
-    for (int g = 0, k = 0; g < d->n_gbufs; g++)
-        for (int c = 0; c < d->h_gch[g]; c++, k++) {
+    p.gbufs = d->t_gbufs; p.NG = d->NG; p.NGX = d->NGX; p.gext = d->d_gext; p.gext_stride = d->gext_stride;
+    for (int g = 0, k = 0; g < d->n_gbufs; g++) {
+        if (d->h_gch[g] != 1 && d->h_gch[g] != 3) continue;  // ignored, as in dr2 (stat_denoiser.cu:103-110)
+        for (int c = 0; c < d->h_gch[g] && k < SMC_MAX_GBUF_CHANNELS; c++, k++) {
             p.g_buf[k] = (unsigned char)g; p.g_ch[k] = (unsigned char)c; p.g_nch[k] = d->h_gch[g];
             p.g_scale[k] = sqrtf(-d->h_gf[g] * 1.4426950408889634f);
         }
+    }
     p.mean_corr = d->t_mc; p.disc = d->t_disc; p.lut = d->ctx->d_lut;
     const size_t row_bytes = smc_rec_row_bytes(d->rec_pitch);
     const smc_denoiser::Peer &up = d->peer[0], &dn = d->peer[1];
@@ -392,17 +419,26 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1) {
     p.peer_down_halo = dn.rec ? dn.rec : nullptr;
     p.peer_up_image_stride = up.image_stride;
     p.peer_down_image_stride = dn.image_stride;
+    if (halo) {
+        p.halo = *halo;
+        // blocks whose row goes into a neighbour: rows [0, r) when a rank sits above, [H - r, H) when one sits below
+        const int r = d->radius, H = d->H;
+        int rows = 0;
+        for (int y = 0; y < H; y++) rows += ((up.rec && y < r) || (dn.rec && y >= H - r)) ? 1 : 0;
+        p.halo_blocks = rows * ((d->rec_pitch + 255) / 256) * d->ptr_count;
+    }
     return smc_launch_prepass(d->ctx, p);
 }
 
 static bool has_peers(const smc_denoiser *d) { return d->peer[0].rec || d->peer[1].rec; }
 
 // filter over output rows [y0, y1)
-static int filter_rows(smc_denoiser *d, int y0, int y1) {
+static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo = nullptr) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
     if (y1 <= y0) return SMC_OK;
     SmcFilterParams p;
     fill_filter_params(d, p);
+    if (halo) p.halo = *halo;
     p.row_begin = y0;
     p.row_end = y1;
     if (d->use_sym) {
@@ -459,15 +495,19 @@ extern "C" int smc_denoiser_prepass(smc_denoiser *d) {
     if (!has_peers(d)) return prepass_rows(d, 0, d->H);
     // Halo protocol, step k: the neighbours must have finished FILTERING step k-1 before their halo rows are overwritten
     // (they signal free_from_* = k-1 into OUR flags); after the prepass (own records + halo rows stored into the
-    // neighbours' arrays) tell them their halos of step k are ready.
+    // neighbours' arrays) tell them their halos of step k are ready.  Both ends live inside the prepass kernel: the blocks
+    // that store into a neighbour wait for its flag, the last of them to retire signals (SmcHaloSync).
     d->step++;
-    int rc = smc_launch_halo_wait(d->ctx, d->peer[0].rec ? d->d_flags + 2 : nullptr, d->peer[1].rec ? d->d_flags + 3 : nullptr,
-                                  d->step - 1);
-    if (rc) return rc;
-    if ((rc = prepass_rows(d, 0, d->H))) return rc;
+    SmcHaloSync h;
+    h.wait0 = d->peer[0].rec ? d->d_flags + 2 : nullptr;
+    h.wait1 = d->peer[1].rec ? d->d_flags + 3 : nullptr;
+    h.wait_value = d->step - 1;
     // the rank above sees us as "down", the rank below as "up"
-    return smc_launch_halo_signal(d->ctx, d->peer[0].flags ? d->peer[0].flags + 1 : nullptr,
-                                  d->peer[1].flags ? d->peer[1].flags + 0 : nullptr, d->step);
+    h.signal0 = d->peer[0].flags ? d->peer[0].flags + 1 : nullptr;
+    h.signal1 = d->peer[1].flags ? d->peer[1].flags + 0 : nullptr;
+    h.signal_value = d->step;
+    h.done_counter = d->d_sync_counters + 0;
+    return prepass_rows(d, 0, d->H, &h);
 }
 
 extern "C" int smc_denoiser_prepass_rows(smc_denoiser *d, int row_begin, int row_end) {
@@ -481,12 +521,22 @@ extern "C" int smc_denoiser_filter(smc_denoiser *d) {
     if (!d) SMC_FAIL(SMC_ERR_INVALID, "NULL plan");
     if (!has_peers(d)) return filter_rows(d, d->row_begin, d->row_end);
     // wait until both neighbours have stored this step's halo rows into our array, filter, then release their halos
-    int rc = smc_launch_halo_wait(d->ctx, d->peer[0].rec ? d->d_flags + 0 : nullptr, d->peer[1].rec ? d->d_flags + 1 : nullptr,
-                                  d->step);
+    SmcHaloSync h;
+    h.wait0 = d->peer[0].rec ? d->d_flags + 0 : nullptr;
+    h.wait1 = d->peer[1].rec ? d->d_flags + 1 : nullptr;
+    h.wait_value = d->step;
+    h.signal0 = d->peer[0].flags ? d->peer[0].flags + 3 : nullptr;
+    h.signal1 = d->peer[1].flags ? d->peer[1].flags + 2 : nullptr;
+    h.signal_value = d->step;
+    h.done_counter = d->d_sync_counters + 1;
+    SmcFilterParams fp;
+    fill_filter_params(d, fp);
+    if (d->use_sym || (d->use_stream && smc_filter_stream_syncs_halo(fp, d->py)))
+        return filter_rows(d, d->row_begin, d->row_end, &h);  // the kernel waits and signals itself
+    int rc = smc_launch_halo_wait(d->ctx, h.wait0, h.wait1, h.wait_value);
     if (rc) return rc;
     if ((rc = filter_rows(d, d->row_begin, d->row_end))) return rc;
-    return smc_launch_halo_signal(d->ctx, d->peer[0].flags ? d->peer[0].flags + 3 : nullptr,
-                                  d->peer[1].flags ? d->peer[1].flags + 2 : nullptr, d->step);
+    return smc_launch_halo_signal(d->ctx, h.signal0, h.signal1, h.signal_value);
 }
 
 extern "C" int smc_denoiser_filter_rows(smc_denoiser *d, int row_begin, int row_end) {
@@ -822,33 +872,36 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
     SMC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
 
-    // The kernel variant depends on the G-buffer channel counts, which live on the device: read them back once per
-    // distinct (pointer, count, shape) and cache the plan on the context (Estimator never changes them after
-    // AllocateBuffers, estimator.cpp:271-288).
-    std::vector<unsigned char> key(sizeof(void *) * 2 + sizeof(int) * 8 + sizeof(float));
+    // The kernel variant and the record packing depend on the G-buffer channel counts and range factors, which live on the
+    // device.  They are read back on EVERY call (a few bytes; the reference's flow blocks in Synchronize() right after
+    // Denoise anyway, statpath.cpp:406-418) and are part of the plan's cache key, so a second Estimator whose tables land on
+    // recycled addresses with other contents can never run with a stale plan.
+    std::vector<unsigned char> gch(std::max(n_gbufs, 1));
+    std::vector<float> gf(std::max(n_gbufs, 1));
+    if (n_gbufs > 0) {
+        SMC_CUDA(cudaMemcpyAsync(gch.data(), gbuf_channel_counts, n_gbufs, cudaMemcpyDeviceToHost, s));
+        SMC_CUDA(cudaMemcpyAsync(gf.data(), gbuf_dr_factors, sizeof(float) * n_gbufs, cudaMemcpyDeviceToHost, s));
+        SMC_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<unsigned char> key(sizeof(int) * 8 + sizeof(float) + (size_t)n_gbufs * (1 + sizeof(float)));
     {
         unsigned char *k = key.data();
-        std::memcpy(k, &gbuf_channel_counts, sizeof(void *)); k += sizeof(void *);
-        std::memcpy(k, &gbuf_dr_factors, sizeof(void *)); k += sizeof(void *);
         const int ints[8] = {channels, ptr_count, width, height, radius, denoise_film, n_gbufs, 0};
         std::memcpy(k, ints, sizeof(ints)); k += sizeof(ints);
-        std::memcpy(k, &ds_factor, sizeof(float));
+        std::memcpy(k, &ds_factor, sizeof(float)); k += sizeof(float);
+        if (n_gbufs > 0) {
+            std::memcpy(k, gch.data(), n_gbufs); k += n_gbufs;
+            std::memcpy(k, gf.data(), sizeof(float) * n_gbufs);
+        }
     }
     const int slot = channels == 3 ? 1 : 0;
     smc_denoiser *d = ctx->cached[slot];
     if (!d || key != ctx->cached_key[slot]) {
         if (d) smc_denoiser_destroy(d);
         ctx->cached[slot] = nullptr;
-        std::vector<unsigned char> gch(std::max(n_gbufs, 1));
-        std::vector<float> gf(std::max(n_gbufs, 1));
-        if (n_gbufs > 0) {
-            SMC_CUDA(cudaMemcpyAsync(gch.data(), gbuf_channel_counts, n_gbufs, cudaMemcpyDeviceToHost, s));
-            SMC_CUDA(cudaMemcpyAsync(gf.data(), gbuf_dr_factors, sizeof(float) * n_gbufs, cudaMemcpyDeviceToHost, s));
-            SMC_CUDA(cudaStreamSynchronize(s));
-        }
         int ng = 0;
         for (int g = 0; g < n_gbufs; g++) {
-            if (gch[g] != 1 && gch[g] != 3) SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d has %d channels", g, gch[g]);
+            if (gch[g] != 1 && gch[g] != 3) continue;  // ignored, as in dr2 (stat_denoiser.cu:103-110)
             if (!(gf[g] <= 0.f)) SMC_FAIL(SMC_ERR_INVALID, "G-buffer %d: drFactor %g must be <= 0", g, gf[g]);
             ng += gch[g];
         }
@@ -856,7 +909,8 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
         d = new (std::nothrow) smc_denoiser;
         if (!d) SMC_FAIL(SMC_ERR_NOMEM, "out of host memory");
         d->ctx = ctx; d->C = channels; d->ptr_count = ptr_count; d->W = width; d->H = height; d->radius = radius;
-        d->denoise_film = denoise_film ? 1 : 0; d->mode = SMC_MEMBER_WELCH; d->n_gbufs = n_gbufs; d->NG = ng;
+        d->denoise_film = denoise_film ? 1 : 0; d->mode = SMC_MEMBER_WELCH; d->n_gbufs = n_gbufs;
+        d->NG = std::min(ng, SMC_REC_GBUF_CHANNELS); d->NGX = ng - d->NG;
         d->row_begin = 0; d->row_end = height; d->ds_factor = ds_factor; d->tables_external = true;
         if (cudaMalloc(&d->d_gch, std::max(n_gbufs, 1)) != cudaSuccess ||
             cudaMalloc(&d->d_gf, sizeof(float) * std::max(n_gbufs, 1)) != cudaSuccess) {

@@ -38,6 +38,16 @@ __global__ void __launch_bounds__(256) filter_generic_kernel(SmcFilterParams p) 
     SmcCentre<C, NG> c;
     smc_make_centre<C, NG, MODE>(rc, c);
 
+    // G-buffer channels beyond the record's seven (SmcFilterParams::gext)
+    constexpr int kMaxX = SMC_MAX_GBUF_CHANNELS - SMC_REC_GBUF_CHANNELS;
+    float gxc[kMaxX];
+    const size_t gx_row = (size_t)p.rec_pitch * p.gext_stride;
+    if (p.NGX > 0) {
+        const float *e = p.gext + (size_t)(y + r) * gx_row + (size_t)(x + p.padX) * p.gext_stride;
+#pragma unroll
+        for (int k = 0; k < kMaxX; k++) gxc[k] = k < p.NGX ? __ldg(e + k) : 0.f;
+    }
+
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, ns = 0.f, den = 0.f;
     int accepted = 0;
     for (int dy = -r; dy < r; dy++) {
@@ -52,7 +62,19 @@ __global__ void __launch_bounds__(256) filter_generic_kernel(SmcFilterParams p) 
                 w = 1.f;  // is_center, stat_denoiser.cu:78, :250-254
             } else {
                 if (!smc_member<C, NG, MODE>(c, ri)) continue;
-                w = smc_weight<C, NG>(c, ri, sw);
+                float swx = sw;
+                if (p.NGX > 0) {  // the further channels' squared differences join the exponent
+                    const float *e = p.gext + (size_t)(y + dy + r) * gx_row + (size_t)(x + dx + p.padX) * p.gext_stride;
+                    float ax = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kMaxX; k++)
+                        if (k < p.NGX) {
+                            const float dgk = __fsub_rn(__ldg(e + k), gxc[k]);
+                            ax = __fmaf_rn(dgk, dgk, ax);
+                        }
+                    swx = __fsub_rn(sw, ax);
+                }
+                w = smc_weight<C, NG>(c, ri, swx);
             }
             if (C == 3 || film_out) {
                 n0 = __fmaf_rn(w, ri.c2.x, n0);

@@ -490,8 +490,14 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ int warps_done;
+    if (threadIdx.x == 0) {
+        warps_done = 0;
+        smc_halo_wait(p.halo);  // multi-GPU: the neighbours' prepasses have stored this step's halo records into our array
+    }
     __syncthreads();  // the only CTA-wide synchronisation
 
+    [&]() {  // the warp's work; returns when the queue is empty
     const int r = p.radius;
     const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
     const int total_warps = (int)gridDim.x * g.nwarps;
@@ -619,6 +625,10 @@ __global__ void __launch_bounds__(kWMaxThreads, 1) filter_warp_kernel(const SmcF
         t_cur = t_next;
         ti = tn;
     }
+    }();
+    // multi-GPU: when the last warp of the last CTA has read its last record, the neighbours may overwrite our halo rows
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&warps_done, 1) == g.nwarps - 1) smc_halo_signal_last(p.halo, (int)gridDim.x);
 }
 
 template <typename K>
@@ -744,9 +754,12 @@ static bool use_warp_variant(const SmcFilterParams &p, int py) {
     return warp_geometry(p, 2, g, smem);
 }
 
+bool smc_filter_stream_syncs_halo(const SmcFilterParams &p, int py) { return use_warp_variant(p, py); }
+
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name) {
     (void)sm_count;
     if (p.C != 3 && p.C != 1) return false;
+    if (p.NGX > 0) return false;  // more G-buffer channels than the record holds: generic kernel
     if (p.radius < 1 || p.radius > 64) return false;
     if (p.sw_margin_y < 3 || p.sw_margin_x < 2) return false;
     if (!(p.NG == 0 || p.NG == 3 || p.NG == 6 || p.NG == 7)) return false;

@@ -120,12 +120,50 @@ __device__ __forceinline__ float sym_weight(const SmcCentre<3, NG> &c, const Smc
     return smc_ex2(-a);
 }
 
+// The membership test (is_not_discriminated, stat_denoiser.cu:81-88: discC + discI <= 2.f * meanC * meanI for every
+// channel; same operands and roundings as smc_member<3, NG, 0>) applied to a weight: returns w if the pair is accepted, else 0.
+// Written as one PTX block -- three chained compares and one select -- so that the weight is computed NEXT TO the test and the
+// eight pair evaluations of a loop iteration stay one straight-line block for the scheduler.  (As `ok ? weight(...) : 0.f` the
+// weight chain is predicated on the test and the pairs serialise two by two; as `ok ? w : 0.f` on a bool the select is
+// distributed over the three compares: three selects.  Measured at 4K: 7.6 / 8.0 ms against ... for this form.)
+template <int NG>
+__device__ __forceinline__ float sym_gate(const SmcCentre<3, NG> &c, const SmcRec &r, float w, int *ok) {
+    const float2 sd = smc_add2(c.d01, make_float2(r.c0.z, r.c0.w));
+    const float2 pm = smc_mul2(c.t01, make_float2(r.c0.x, r.c0.y));
+    const float sz = __fadd_rn(c.dz, r.c1.y);
+    const float pz = __fmul_rn(c.tz, r.c1.x);
+    float g;
+    if (ok) {
+        asm("{\n"
+            ".reg .pred p;\n"
+            "setp.le.f32 p, %2, %3;\n"
+            "setp.le.and.f32 p, %4, %5, p;\n"
+            "setp.le.and.f32 p, %6, %7, p;\n"
+            "selp.f32 %0, %8, 0f00000000, p;\n"
+            "selp.s32 %1, 1, 0, p;\n"
+            "}\n"
+            : "=f"(g), "=r"(*ok)
+            : "f"(sd.x), "f"(pm.x), "f"(sd.y), "f"(pm.y), "f"(sz), "f"(pz), "f"(w));
+    } else {
+        asm("{\n"
+            ".reg .pred p;\n"
+            "setp.le.f32 p, %1, %2;\n"
+            "setp.le.and.f32 p, %3, %4, p;\n"
+            "setp.le.and.f32 p, %5, %6, p;\n"
+            "selp.f32 %0, %7, 0f00000000, p;\n"
+            "}\n"
+            : "=f"(g)
+            : "f"(sd.x), "f"(pm.x), "f"(sd.y), "f"(pm.y), "f"(sz), "f"(pz), "f"(w));
+    }
+    return g;
+}
+
 // One pair evaluation, booked both ways (forward to the centre, mirror to the record).  A rejected pair takes part with
 // weight 0 (one select) instead of predicating the four accumulations.
 template <int NG, bool COUNT>
 __device__ __forceinline__ void pair_sym(SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
-    const bool ok = smc_member<3, NG, 0>(s.c, r);
-    const float w = ok ? sym_weight<NG>(s.c, r, nsw) : 0.f;
+    int ok = 0;
+    const float w = sym_gate<NG>(s.c, r, sym_weight<NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
     const float2 ww = make_float2(w, w);  // folded by ptxas into the scalar-broadcast operand form of FFMA2
     s.n01 = smc_fma2(ww, make_float2(r.c2.x, r.c2.y), s.n01);
     if (NG <= 6) {
@@ -149,8 +187,8 @@ __device__ __forceinline__ void pair_sym(SymCentre<3, NG> &s, const SmcRec &r, f
 // The two forward offsets that are taps of the record's window only: booked to the record.
 template <int NG, bool COUNT>
 __device__ __forceinline__ void pair_mirror_only(const SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
-    const bool ok = smc_member<3, NG, 0>(s.c, r);
-    const float w = ok ? sym_weight<NG>(s.c, r, nsw) : 0.f;
+    int ok = 0;
+    const float w = sym_gate<NG>(s.c, r, sym_weight<NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
     const float2 ww = make_float2(w, w);
     m.m01 = smc_fma2(ww, s.v01, m.m01);
     if (NG <= 6) {
@@ -329,8 +367,14 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ int warps_done;
+    if (threadIdx.x == 0) {
+        warps_done = 0;
+        smc_halo_wait(p.halo);  // multi-GPU: the neighbours' prepasses have stored this step's halo records into our array
+    }
     __syncthreads();  // the only CTA-wide synchronisation
 
+    [&]() {  // the warp's work; returns when the queue is empty
     const int r = p.radius;
     const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
     const int total_warps = (int)gridDim.x * g.nwarps;
@@ -497,6 +541,10 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
     }
     // the scratch is read by the gather kernel: every store of this warp must have landed
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }();
+    // multi-GPU: when the last warp of the last CTA has read its last record, the neighbours may overwrite our halo rows
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&warps_done, 1) == g.nwarps - 1) smc_halo_signal_last(p.halo, (int)gridDim.x);
 }
 
 // out(y, x) = (forward sums + every partial mirror sum that covers the pixel) / den   (stat_denoiser.cu:341-344)
@@ -558,7 +606,7 @@ int launch_sym_ng(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams
 bool smc_filter_sym_supported(const SmcFilterParams &p) {
     if (p.C != 3 || p.mode != SMC_MEMBER_WELCH) return false;  // the Moon test is not symmetric (stat_denoiser.cu:132-143)
     if (p.radius < 2 || p.radius > SMC_MAX_RADIUS) return false;
-    if (p.NG < 0 || p.NG > 7) return false;
+    if (p.NG < 0 || p.NG > 7 || p.NGX > 0) return false;
     if ((p.padX & 1) || (p.rec_pitch & 1)) return false;
     const int xorg = -(p.radius + (p.radius & 1));
     if (xorg + p.padX - p.radius < 0) return false;  // the first strip's record segment starts inside the padded array

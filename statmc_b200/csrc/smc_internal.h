@@ -58,6 +58,7 @@ static_assert(sizeof(SmcPtrStepSz) == 24, "must match cv::cuda::PtrStepSzb");
 // two apart (the streaming filter's mapping) every LDS.128 is bank-conflict-free, and -- unlike an XOR swizzle --
 // the chunk addresses of a record stay an affine function of its index: no per-load integer math in the inner loop.
 // A record row is laid out identically in HBM and in shared memory, so a row segment moves with one bulk copy.
+#define SMC_REC_GBUF_CHANNELS 7  // G-buffer channels inside the record; further ones live in the extension array
 #define SMC_REC_FLOATS 16
 #define SMC_REC_BYTES 64
 #define SMC_LINE_BYTES 144
@@ -97,6 +98,42 @@ struct smc_buffer {
     size_t elem_bytes;  // bytes per pixel
 };
 
+// Cross-GPU halo protocol folded into the kernels (multi-GPU peer halos; all null / zero otherwise).  A kernel first WAITS --
+// one thread per block spins with acquire loads at system scope until both flags have reached `wait_value` -- and, when its
+// last block retires (device-scope counter), SIGNALS: release stores of `signal_value` at system scope into the neighbours'
+// flags.  Replaces four single-thread kernels per step.
+struct SmcHaloSync {
+    const int *wait0, *wait1;
+    int wait_value;
+    int *signal0, *signal1;
+    int signal_value;
+    int *done_counter;  // blocks retired so far; reset by the last one
+};
+
+__device__ __forceinline__ void smc_halo_wait(const SmcHaloSync &h) {  // call from ONE thread, then barrier
+    for (int k = 0; k < 2; k++) {
+        const int *f = k ? h.wait1 : h.wait0;
+        if (!f) continue;
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v < h.wait_value) __nanosleep(100);
+        } while (v < h.wait_value);
+    }
+}
+// call from ONE thread of every participating block after the block's work (and a block barrier); `total` blocks take part
+__device__ __forceinline__ void smc_halo_signal_last(const SmcHaloSync &h, int total) {
+    if (!h.signal0 && !h.signal1) return;
+    __threadfence_system();
+    const int done = atomicAdd(h.done_counter, 1) + 1;
+    if (done == total) {
+        *h.done_counter = 0;
+        __threadfence_system();
+        if (h.signal0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(h.signal0), "r"(h.signal_value) : "memory");
+        if (h.signal1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(h.signal1), "r"(h.signal_value) : "memory");
+    }
+}
+
 // filter parameters shared by the kernels (passed by value)
 struct SmcFilterParams {
     int W, H;              // local plane size
@@ -116,6 +153,11 @@ struct SmcFilterParams {
     const SmcPtrStepSz *out_ptrs;  // film_filtered_ptrs table (device)
     SmcPtrStepSz film_filtered;    // "film-f"
     const SmcPtrStepSz *accepted;  // optional, may be null
+    // G-buffer channels beyond the seven of the record (generic kernel only): [record row][padded column][gext_stride] floats,
+    // pre-scaled like the record's; shared by all images
+    const float *gext;
+    int NGX, gext_stride;
+    SmcHaloSync halo;              // wait for the neighbours' halo records, release ours when done (sym / per-warp kernels)
     int *tile_counter;             // streaming kernel: global tile counter (dynamic scheduling), reset before each launch
     unsigned long long *trace;     // debug (SMC_STREAM_TRACE): per CTA {start ns, end ns, smid, tiles}; normally null
 };
@@ -156,14 +198,20 @@ struct SmcPrepassParams {
     // (its padded rows [H_up + r, H_up + 2r)) and the top halo of the rank below (its padded rows [0, r)).
     unsigned char *peer_up_halo, *peer_down_halo;   // address of the first halo row of image 0 in the peer's array, or null
     size_t peer_up_image_stride, peer_down_image_stride;
+    // blocks that store into a neighbour wait until it has released its halo rows (wait0: rank above, wait1: rank below) and
+    // the last of them tells both neighbours that their halos are complete
+    SmcHaloSync halo;
+    int halo_blocks;
     const SmcPtrStepSz *n, *mean, *m2, *m3, *film_ptrs;
     SmcPtrStepSz film;
     const SmcPtrStepSz *gbufs;           // G-buffer plane descriptors (device table)
     // flattened G-buffer channels (by value): channel k of the record comes from plane g_buf[k], component g_ch[k] of
     // g_nch[k], multiplied by g_scale[k] = sqrtf(-drFactor * log2(e))
-    int NG;
-    unsigned char g_buf[7], g_ch[7], g_nch[7];
-    float g_scale[7];
+    int NG;                       // channels packed into the record (<= 7)
+    int NGX, gext_stride;         // further channels, written to `gext` (see SmcFilterParams)
+    float *gext;
+    unsigned char g_buf[SMC_MAX_GBUF_CHANNELS], g_ch[SMC_MAX_GBUF_CHANNELS], g_nch[SMC_MAX_GBUF_CHANNELS];
+    float g_scale[SMC_MAX_GBUF_CHANNELS];
     const SmcPtrStepSz *mean_corr, *disc;  // optional tables (device) or null
     const float *lut;
 };
@@ -180,6 +228,8 @@ int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const i
 // the width in pixels of the tile one worker owns
 int smc_filter_stream_resident_ctas(const SmcFilterParams &p, int py, int sm_count, int *tile_w);
 bool smc_filter_stream_supported(const SmcFilterParams &p, int sm_count, const char **name);
+// true when the streaming variant that would run handles SmcFilterParams::halo itself (the per-warp kernel)
+bool smc_filter_stream_syncs_halo(const SmcFilterParams &p, int py);
 // symmetric kernel: every unordered pair evaluated once (RGB statistics, Welch membership, any radius 2..255, any NG)
 bool smc_filter_sym_supported(const SmcFilterParams &p);
 bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &smem);

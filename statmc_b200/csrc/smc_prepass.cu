@@ -37,14 +37,40 @@ __device__ __forceinline__ float lut_t(const float *__restrict__ lut, int idx) {
 // HBM bandwidth, not by load latency or the XU pipe (the twelve IEEE divisions of a pixel share three divisors, see
 // smc_fastdiv.cuh).
 template <int C, int NG>
+__device__ __forceinline__ void prepass_pixel(const SmcPrepassParams &p, const int pc, const int pr, const int z);
+
+template <int C, int NG>
 __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     const int col_blocks = (p.rec_pitch + blockDim.x - 1) / blockDim.x;
     const int pc = (blockIdx.x % col_blocks) * blockDim.x + threadIdx.x;  // padded column
     const int pr = p.pr_begin + blockIdx.x / col_blocks;                   // padded row: y = pr - radius
     const int z = blockIdx.y;
-    if (pc >= p.rec_pitch) return;
     const int yy = pr - p.radius;
-    if ((yy < 0 && p.skip_top) || (yy >= p.H && p.skip_bottom)) return;
+    // multi-GPU: this block's row also goes into a neighbour's halo -> wait until that neighbour has filtered the previous step
+    const bool to_up = p.peer_up_halo && yy >= 0 && yy < p.radius && yy < p.H;
+    const bool to_dn = p.peer_down_halo && yy >= p.H - p.radius && yy >= 0 && yy < p.H;
+    if ((to_up || to_dn) && (p.halo.wait0 || p.halo.wait1)) {
+        if (threadIdx.x == 0) {
+            SmcHaloSync h = p.halo;
+            if (!to_up) h.wait0 = nullptr;
+            if (!to_dn) h.wait1 = nullptr;
+            smc_halo_wait(h);
+        }
+        __syncthreads();
+    }
+    const bool idle = pc >= p.rec_pitch || (yy < 0 && p.skip_top) || (yy >= p.H && p.skip_bottom);
+    if (idle && !(to_up || to_dn)) return;
+    if (!idle) prepass_pixel<C, NG>(p, pc, pr, z);
+    if (to_up || to_dn) {  // block-uniform
+        __threadfence_system();  // this thread's peer stores before the block's signal
+        __syncthreads();
+        if (threadIdx.x == 0) smc_halo_signal_last(p.halo, p.halo_blocks);
+    }
+}
+
+template <int C, int NG>
+__device__ __forceinline__ void prepass_pixel(const SmcPrepassParams &p, const int pc, const int pr, const int z) {
+    const int yy = pr - p.radius;
     const int y = min(max(yy, 0), p.H - 1);
     const int x = min(max(pc - p.padX, 0), p.W - 1);
     const bool own = (yy == y) && (pc - p.padX == x);  // not a replicated copy: also writes the API-visible planes
@@ -155,6 +181,14 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
 #pragma unroll
     for (int c = 0; c < 4; c++)
         *(float4 *)(row + smc_rec_chunk_offset(pc, c)) = make_float4(rec[4 * c], rec[4 * c + 1], rec[4 * c + 2], rec[4 * c + 3]);
+    // G-buffer channels that do not fit the record (more than seven): side array, read by the generic filter kernel
+    if (p.NGX > 0 && z == 0) {
+        float *e = p.gext + ((size_t)pr * p.rec_pitch + pc) * p.gext_stride;
+        for (int k = 0; k < p.NGX; k++) {
+            const int kk = SMC_REC_GBUF_CHANNELS + k;
+            e[k] = __fmul_rn(rowf(p.gbufs[p.g_buf[kk]], y)[x * p.g_nch[kk] + p.g_ch[kk]], p.g_scale[kk]);
+        }
+    }
     // halo exchange fused into the producer: the same record goes to the neighbouring GPUs that need it (peer stores)
     if (yy == y) {
         unsigned char *peer = nullptr;

@@ -95,11 +95,33 @@ def test_nan_pixels_pass_through(ctx):
         assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
 
 
-@pytest.mark.parametrize("names", [(), ("normal",), ("normal", "albedo", "depth"), ("depth",), ("depth", "albedo")])
+@pytest.mark.parametrize("names", [(), ("normal",), ("normal", "albedo", "depth"), ("depth",), ("depth", "albedo"),
+                                   ("depth", "normal"), ("depth", "depth"), ("normal", "depth", "depth")])
 def test_gbuffer_sets(ctx, names):
-    # scalar G-buffers (depth) work in the kernel but are broken on the reference's host side
+    # scalar G-buffers (depth) work in the kernel but are broken on the reference's host side;
+    # every flattened channel count 0..7 has a symmetric-kernel instantiation
     b = small_buffers(80, 33)
-    _check(ctx, b, 6, 3.0, 0, gbuf_names=names)
+    ours, _ = _check(ctx, b, 6, 3.0, 0, gbuf_names=names)
+    assert "sym" in ours["kernel"]
+
+
+@pytest.mark.parametrize("names", [("depth", "depth", "normal", "albedo"), ("normal", "albedo", "normal", "albedo", "depth")])
+def test_more_than_seven_gbuffer_channels(ctx, names):
+    # filterbuffers [materialid depth normal albedo] = 1 + 1 + 3 + 3 = 8 flattened channels is a valid reference
+    # configuration (statpath.cpp:1095-1155; dr2 loops over any number of buffers, stat_denoiser.cu:101-111): the channels
+    # beyond the record's seven travel in a side array and the generic kernel filters
+    b = small_buffers(80, 33)
+    ours, _ = _check(ctx, b, 6, 3.0, 0, gbuf_names=names)
+    assert "generic" in ours["kernel"]
+
+
+def test_gbuffer_with_other_channel_count_is_ignored(ctx):
+    # dr2 only knows 3- and 1-channel buffers and silently skips anything else (stat_denoiser.cu:103-110)
+    b = small_buffers(80, 33)
+    b["two"] = np.ascontiguousarray(b["normal"][..., :2])
+    ours = denoise_host(ctx, b, radius=6, sd=3.0, gbuf_names=("normal", "two", "albedo"), gbuf_sds={"two": 0.05}, want_aux=True)
+    ora = po.denoise(b, radius=6, sd=3.0, precision="f64", want_aux=True)
+    assert np.array_equal(ours["accepted"], ora["accepted"]) and rel_mad(ours["film_f"], ora["film_f"]) <= TOL
 
 
 def test_tiny_and_degenerate_shapes(ctx):

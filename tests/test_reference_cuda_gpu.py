@@ -11,16 +11,19 @@ from util import bits_equal, max_abs, rel_mad
 pytestmark = pytest.mark.gpu
 
 
-def _ref_denoise(ctx, b, radius, sd, moon=False, normal_sd=0.1, albedo_sd=0.02):
+SDS = {"normal": 0.1, "albedo": 0.02, "depth": 1.0}
+
+
+def _ref_denoise(ctx, b, radius, sd, moon=False, gbuf_names=("normal", "albedo")):
     H, W = b["n"].shape
     up = lambda a: Buffer.from_array(ctx, a)
-    d = {k: up(b[k]) for k in ("n", "mean", "m2", "m3", "film", "normal", "albedo")}
+    d = {k: up(b[k]) for k in ("n", "mean", "m2", "m3", "film") + tuple(gbuf_names)}
     mc, dc, out, dummy = (Buffer(ctx, H, W, 3) for _ in range(4))
     pl = lambda buf: (buf.plane.dev, buf.plane.step)
-    f = po.RefFilter(3, W, H, -0.5 / (sd * sd), radius, True, [pl(d["n"])], [pl(d["mean"])], [pl(d["m2"])],
-                     [pl(d["m3"])], [pl(d["film"])], pl(d["film"]), [pl(d["normal"]), pl(d["albedo"])], [3, 3],
-                     [-0.5 / normal_sd ** 2, -0.5 / albedo_sd ** 2], [pl(mc)], [pl(dc)], [pl(dummy)], pl(out),
-                     moon=moon)
+    f = po.RefFilter(3, W, H, po.f32_factor(sd), radius, True, [pl(d["n"])], [pl(d["mean"])], [pl(d["m2"])],
+                     [pl(d["m3"])], [pl(d["film"])], pl(d["film"]), [pl(d[k]) for k in gbuf_names],
+                     [1 if b[k].ndim == 2 else 3 for k in gbuf_names], [po.f32_factor(SDS[k]) for k in gbuf_names],
+                     [pl(mc)], [pl(dc)], [pl(dummy)], pl(out), moon=moon)
     ctx.synchronize()
     f.run(0)
     f.synchronize(0)
@@ -35,7 +38,7 @@ def _ref_denoise(ctx, b, radius, sd, moon=False, normal_sd=0.1, albedo_sd=0.02):
 def test_against_reference_kernels(ctx, W, H, radius, sd, n, vary):
     b = synth.moment_buffers(W, H, n=n, config_id=71, vary_n=vary)
     ref = _ref_denoise(ctx, b, radius, sd)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3):
         ours = denoise_host(ctx, b, radius=radius, sd=sd, kernel=kernel, want_aux=True)
         assert bits_equal(ours["mean_corr"], ref["mean_corr"]), "mean-corr differs from johnson_mean_corrs_kernel"
         assert bits_equal(ours["disc"], ref["disc"]), "discriminator differs from mean_discriminators_kernel"
@@ -46,6 +49,25 @@ def test_against_reference_kernels(ctx, W, H, radius, sd, n, vary):
     ora = po.denoise(b, radius=radius, sd=sd, precision="f64", want_aux=True)
     assert bits_equal(ora["mean_corr"], ref["mean_corr"]) and bits_equal(ora["disc"], ref["disc"])
     assert rel_mad(ora["film_f"], ref["film_f"]) <= 1e-5
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref/libstatmc_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("names", [("depth",), ("depth", "albedo"), ("normal", "depth", "albedo"), (),
+                                   ("depth", "depth", "normal", "albedo")])
+def test_scalar_gbuffers_against_reference_kernels(ctx, names):
+    # dr2's 1-channel branch (stat_denoiser.cu:109-110) works in the reference's kernel although its host side never feeds it
+    # (SURVEY.md A16): run the reference kernel itself with scalar G-buffers, and with eight flattened channels
+    b = synth.moment_buffers(150, 70, n=32, config_id=73)
+    ref = _ref_denoise(ctx, b, 9, 4.0, gbuf_names=names)
+    ng = sum(1 if b[k].ndim == 2 else 3 for k in names)
+    for kernel in (0, 1, 2):
+        if kernel == 2 and ng not in (0, 3, 6, 7):
+            continue  # the one-sided streaming kernel is instantiated for these channel counts only
+        ours = denoise_host(ctx, b, radius=9, sd=4.0, kernel=kernel, gbuf_names=names, want_aux=True)
+        assert bits_equal(ours["disc"], ref["disc"])
+        rm = rel_mad(ours["film_f"], ref["film_f"])
+        print("scalar G-buffers %s vs reference CUDA: kernel=%s relMAD=%.3e" % (names, ours["kernel"], rm))
+        assert rm <= 1e-4
 
 
 @pytest.mark.skipif(not po.ref_available(moon=True), reason="oracle/_ref/libstatmc_ref_moon.so not built")
