@@ -466,6 +466,55 @@ def parity_check(env, workload, radius, make_plan, step, out_timed, lo, y0, y1):
     return res
 
 
+def run_acrr_leg(env, steps=10):
+    """ptrCount > 1: the reference's ACRR configuration (scenes/acrr.pbrt: multichannelstats false, trackedbounces 5,
+    denoiseimage false) -- five scalar per-bounce images filtered in one filter<float> call, sharing the G-buffers
+    (stat_denoiser.cu:422 grid.z, estimator.cpp:225-229) -- at 1920x1080, r = 20, sd = 10.  Device-resident timing and a
+    crop of image 0 against the float64 transcription."""
+    from oracle import pyoracle as po
+    from statmc_b200 import synth
+    from statmc_b200.api import Buffer, Denoiser
+    ctx = env.ctx
+    W, H, radius, sd, n, Z = 1920, 1080, 20, 10.0, 64, 5
+    b = synth.moment_buffers(W, H, n=n, config_id=7)
+    chan = lambda a, z: np.ascontiguousarray(a[..., z % 3] * np.float32(1.0 + 0.25 * (z // 3)))
+    imgs = [{k: Buffer.from_array(ctx, chan(b[k], z)) for k in ("mean", "m2", "m3", "film")} for z in range(Z)]
+    nbuf = Buffer.from_array(ctx, b["n"])
+    g = [Buffer.from_array(ctx, b["normal"]), Buffer.from_array(ctx, b["albedo"])]
+    outs = [Buffer(ctx, H, W, 1, np.float32) for _ in range(Z)]
+    dn = Denoiser(ctx, channels=1, width=W, height=H, radius=radius, ds_factor=f32_factor(sd), n=[nbuf] * Z,
+                  mean=[i["mean"] for i in imgs], m2=[i["m2"] for i in imgs], m3=[i["m3"] for i in imgs],
+                  film_ptrs=[i["film"] for i in imgs], gbufs=g, gbuf_dr_factors=[f32_factor(NORMAL_SD), f32_factor(ALBEDO_SD)],
+                  film_filtered_ptrs=outs, denoise_film=False)
+    for _ in range(3):
+        dn.run()
+    env.barrier()
+    a, e = env.ev(), env.ev()
+    a.record()
+    for _ in range(steps):
+        dn.run()
+    e.record()
+    env.barrier()
+    ms = a.elapsed_time(e) / steps
+    # parity of image 0 on an interior crop
+    y0, x0, ch, cw = 500, 900, 16, 96
+    sl = (slice(y0 - radius, y0 + ch + radius), slice(x0 - radius, x0 + cw + radius))
+    sub = {k: np.ascontiguousarray(v[sl]) for k, v in b.items()}
+    mc, dc = po.prepass(sub["n"], chan(sub["mean"], 0), chan(sub["m2"], 0), chan(sub["m3"], 0))
+    ref = po.filter(chan(sub["film"], 0), [sub["normal"], sub["albedo"]], [f32_factor(NORMAL_SD), f32_factor(ALBEDO_SD)], radius,
+                    f32_factor(sd), mean_corr=mc, disc=dc, precision="f64")
+    got = outs[0].download(y0, ch)[:, x0:x0 + cw].astype(np.float64)
+    r64 = np.asarray(ref)[radius:radius + ch, radius:radius + cw].astype(np.float64)
+    rel = float(np.mean(np.abs(got - r64)) / np.mean(np.abs(r64)))
+    res = {"config": "5 scalar per-bounce images + shared normal/albedo G-buffers (scenes/acrr.pbrt: trackedbounces 5, "
+                     "multichannelstats false, denoiseimage false), %dx%d, r=%d sd=%g" % (W, H, radius, sd),
+           "images": Z, "value": Z * W * H / (ms * 1e-3) / 1e6, "unit": "image-Mpix/s", "ms_per_step": ms, "steps": steps,
+           "kernel": dn.kernel_name, "record_bytes_per_px_per_image": 72,
+           "parity": {"rel_mad": rel, "tol": PARITY_TOL, "ok": bool(rel <= PARITY_TOL), "crop_px": ch * cw}}
+    dn.close()
+    return res
+
+
 def run_accum_leg(env, W, rows):
     """Secondary metric: stat-accum Gsamples/s (stage 1) on this rank's band."""
     from statmc_b200.api import MomentState
@@ -491,8 +540,39 @@ def run_accum_leg(env, W, rows):
     rl = {"bound": "hbm", "achieved": bytes_per_launch / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
           "frac": bytes_per_launch / t / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": bytes_per_launch}
     rl.update(ncu_traffic("accum", env.world == 1 and srows == 1080 and W == 3840))
-    del smp
-    return {"value": nsmp / t / 1e9, "unit": "Gsamples/s", "batch": S, "pixels_per_gpu": srows * W, "roofline": rl}
+    del smp, st
+    res = {"value": nsmp / t / 1e9, "unit": "Gsamples/s", "batch": S, "pixels_per_gpu": srows * W, "roofline": rl,
+           "samples": "uniform(0.01, 4): the easy case"}
+    if env.world == 1:
+        # the hard case: BASELINE configs[4]'s heavy-tailed stream (Gamma(k = .25) radiance, x1000 caustic spike with
+        # p = 1/512, as statmc_b200/synth.py draws it) at several batch sizes; `fallback_share` = updates that left the
+        # kernel's fast path for its scalar IEEE path
+        sweep = []
+        for S2 in (4, 16, 64, 256):
+            rows2 = int(max(8, min(1080, 6e9 // (S2 * W * 12))))
+            st2 = MomentState(env.ctx, W, rows2, 3, transform=True)
+            x = torch._standard_gamma(torch.full((S2, rows2, W, 3), 0.25, dtype=torch.float32, device="cuda")) * 4.0
+            spike = torch.rand((S2, rows2, W, 1), device="cuda") < (1.0 / 512.0)
+            x = torch.where(spike, x * 1000.0, x).contiguous()
+            del spike
+            st2.add_samples_dev(x.data_ptr(), S2)
+            env.ctx.accumulate_fallback_samples()
+            st2.add_samples_dev(x.data_ptr(), S2)
+            slow = env.ctx.accumulate_fallback_samples() / float(S2 * rows2 * W)
+            a, b = env.ev(), env.ev()
+            reps2 = 5 if S2 <= 64 else 2
+            a.record()
+            for _ in range(reps2):
+                st2.add_samples_dev(x.data_ptr(), S2)
+            b.record()
+            torch.cuda.synchronize()
+            t2 = a.elapsed_time(b) / reps2 * 1e-3
+            by = S2 * rows2 * W * 12 + rows2 * W * 128
+            sweep.append({"batch": S2, "rows": rows2, "gsamples_per_s": S2 * rows2 * W / t2 / 1e9,
+                          "hbm_frac": by / t2 / 1e9 / pk["hbm_gbs"], "fallback_share": slow})
+            del x, st2
+        res["heavy_tail_sweep"] = sweep
+    return res
 
 
 def main():
@@ -517,6 +597,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-8k", action="store_true", help="skip the second leg (BASELINE configs[3]: 8K, r=40)")
+    ap.add_argument("--no-acrr", action="store_true", help="skip the ptrCount > 1 leg (five scalar per-bounce images)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.channels == 1:
@@ -537,6 +618,7 @@ def main():
                                want_e2e=not args.no_e2e, sample_clocks=True)
     W, H, radius, sd, n = main_leg["W"], main_leg["H"], main_leg["radius"], main_leg["sd"], main_leg["n"]
     accum = None if args.no_accum else run_accum_leg(env, W, main_leg["rows"])
+    acrr = None
     leg8k = None
     default_run = args.workload == "4k" and not args.radius and args.channels == 3 and args.gbufs == 2 and args.kernel == 0
     if default_run and not args.no_8k:
@@ -547,6 +629,8 @@ def main():
                  "filter_ms": l8["filt_ms"], "prepass_ms": l8["pre_ms"], "kernel": l8["kernel"], "parity": l8.get("parity"),
                  "scaling": "strong", "efficiency_inputs": "value at each N of the scaling run; efficiency(N) = value(N) / (N * value(1))"}
 
+    if default_run and world == 1 and not args.no_acrr:
+        acrr = run_acrr_leg(env)
     ok = True
     if rank == 0:
         band_px, f_ms, p_ms, pairs = main_leg["band_px"], main_leg["filt_ms"], main_leg["pre_ms"], main_leg["pairs"]
@@ -588,14 +672,14 @@ def main():
                      "frac": fp32_ach / fp32_peak, "frac_at_observed_clock": fp32_ach / (148 * 128 * sm_mhz * 1e6),
                      "gpairs_per_s": pairs / (f_ms * 1e-3) / 1e9},
             "roofline_prepass": roof_pre, "clocks": clocks, "gpu_launches": main_leg["launches"],
-            "parity": main_leg.get("parity"), "e2e": main_leg.get("e2e"), "accum": accum, "config4_8k": leg8k,
+            "parity": main_leg.get("parity"), "e2e": main_leg.get("e2e"), "accum": accum, "config4_8k": leg8k, "acrr": acrr,
         }
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(W, H, radius, sd, n)
             if accum is not None:
                 accum["cpu_baseline"] = cpu_accum_baseline(W)
         print(json.dumps(res), flush=True)
-        for leg in (main_leg.get("parity"), leg8k and leg8k.get("parity")):
+        for leg in (main_leg.get("parity"), leg8k and leg8k.get("parity"), acrr and acrr.get("parity")):
             if leg is not None and not leg["ok"]:
                 ok = False
                 print("bench.py: PARITY FAILURE %s" % json.dumps(leg), file=sys.stderr, flush=True)

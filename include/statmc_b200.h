@@ -88,6 +88,10 @@ void *smc_context_stream(smc_context *ctx); /* the cudaStream_t in use */
 int smc_context_device(smc_context *ctx);
 /* Number of kernels of this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t smc_context_launch_count(smc_context *ctx);
+/* Diagnostic: (pixel, sample) updates that smc_accumulate redid on its scalar IEEE path since the last call (inputs outside
+ * the proven range of the fast path: zero/denormal-scale differences, non-finite values, n >= 2^22).  Synchronises the
+ * context's stream and resets the counter.  Results are bit-identical on either path; this only explains throughput. */
+uint64_t smc_accumulate_fallback_samples(smc_context *ctx);
 
 /* Two-sided significance level of the Student-t quantile table (SD.cu:53-67: "SET DIFFERENT LUTS HERE").
  * Default 0.005 (t_005_quantiles, SD.cu:56,67).  The nine levels the reference carries as text are served from

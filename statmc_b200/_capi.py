@@ -71,6 +71,7 @@ SIGNATURES = {
     "smc_context_stream": (C.c_void_p, [C.c_void_p]),
     "smc_context_device": (C.c_int, [C.c_void_p]),
     "smc_context_launch_count": (C.c_uint64, [C.c_void_p]),
+    "smc_accumulate_fallback_samples": (C.c_uint64, [C.c_void_p]),
     "smc_set_alpha": (C.c_int, [C.c_void_p, C.c_double]),
     "smc_get_alpha": (C.c_double, [C.c_void_p]),
     "smc_get_t_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -41,6 +41,10 @@ class Context:
     def launches(self) -> int:
         return int(lib.smc_context_launch_count(self.h))
 
+    def accumulate_fallback_samples(self) -> int:
+        """(pixel, sample) updates redone on the scalar IEEE path since the last call (diagnostic; synchronises)."""
+        return int(lib.smc_accumulate_fallback_samples(self.h))
+
     def set_alpha(self, alpha: float) -> None:
         check(lib.smc_set_alpha(self.h, float(alpha)))
 

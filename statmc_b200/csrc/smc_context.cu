@@ -176,6 +176,7 @@ extern "C" void smc_context_destroy(smc_context *ctx) {
     for (smc_denoiser *c : ctx->cached)
         if (c) smc_denoiser_destroy(c);
     cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_accum_fallback);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -190,6 +191,16 @@ extern "C" int smc_synchronize(smc_context *ctx) {
 extern "C" void *smc_context_stream(smc_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int smc_context_device(smc_context *ctx) { return ctx ? ctx->device : -1; }
 extern "C" uint64_t smc_context_launch_count(smc_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" uint64_t smc_accumulate_fallback_samples(smc_context *ctx) {
+    if (!ctx || !ctx->d_accum_fallback) return 0;
+    unsigned long long v = 0;
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+    if (cudaMemcpy(&v, ctx->d_accum_fallback, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    cudaMemset(ctx->d_accum_fallback, 0, sizeof(v));
+    return v;
+}
 
 extern "C" int smc_set_alpha(smc_context *ctx, double alpha) {
     if (!ctx) SMC_FAIL(SMC_ERR_INVALID, "ctx == NULL");

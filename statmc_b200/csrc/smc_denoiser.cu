@@ -115,7 +115,7 @@ static int build_sym_table(smc_denoiser *d) {
     SmcFilterParams p;
     std::memset(&p, 0, sizeof(p));
     p.radius = d->radius; p.W = d->W; p.row_begin = d->row_begin; p.row_end = d->row_end; p.ptr_count = d->ptr_count;
-    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = 3;
+    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = d->C;
     SmcSymParams g;
     size_t smem = 0;
     if (!smc_filter_sym_geometry(p, g, smem)) return SMC_OK;  // no symmetric variant for this plan

@@ -67,8 +67,8 @@ __device__ __forceinline__ SmcRec ldg_rec(const unsigned char *row, int pcol) {
 template <int C, int NG>
 struct SymCentre {
     SmcCentre<C, NG> c;
-    float2 v01, v2o;   // (V.x, V.y), (V.z, 1)
-    float2 n01, n2d;   // forward sums: (num.x, num.y), (num.z, den)
+    float2 v01, v2o;   // RGB statistics: (V.x, V.y), (V.z, 1);  scalar statistics: v01.x = the scalar value
+    float2 n01, n2d;   // forward sums: (num.x, num.y), (num.z, den);  scalar statistics: n01.x = num, n2d.y = den
     int cnt;
 };
 
@@ -95,8 +95,8 @@ __device__ __forceinline__ void sym_order() {
 
 // 2^(sw - a), a = sum_k (g'_I,k - g'_C,k)^2, with the table holding (-sw, 0) so that the first squared difference is an FMA
 // onto it (one instruction fewer than smc_weight(); -sw = +inf outside the disc -> weight 0)
-template <int NG>
-__device__ __forceinline__ float sym_weight(const SmcCentre<3, NG> &c, const SmcRec &r, float2 nsw) {
+template <int C, int NG>
+__device__ __forceinline__ float sym_weight(const SmcCentre<C, NG> &c, const SmcRec &r, float2 nsw) {
     float a;
     if (NG >= 2) {
         float2 e = smc_add2(make_float2(r.c2.z, r.c2.w), c.g[0]);
@@ -126,13 +126,27 @@ __device__ __forceinline__ float sym_weight(const SmcCentre<3, NG> &c, const Smc
 // eight pair evaluations of a loop iteration stay one straight-line block for the scheduler.  (As `ok ? weight(...) : 0.f` the
 // weight chain is predicated on the test and the pairs serialise two by two; as `ok ? w : 0.f` on a bool the select is
 // distributed over the three compares: three selects.  Measured at 4K: 7.6 / 8.0 ms against ... for this form.)
-template <int NG>
-__device__ __forceinline__ float sym_gate(const SmcCentre<3, NG> &c, const SmcRec &r, float w, int *ok) {
+template <int C, int NG>
+__device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRec &r, float w, int *ok) {
+    float g;
+    if (C == 1) {  // scalar statistics: one channel
+        const float s0 = __fadd_rn(c.d01.x, r.c0.z), p0 = __fmul_rn(c.t01.x, r.c0.x);
+        int o;
+        asm("{\n"
+            ".reg .pred p;\n"
+            "setp.le.f32 p, %2, %3;\n"
+            "selp.f32 %0, %4, 0f00000000, p;\n"
+            "selp.s32 %1, 1, 0, p;\n"
+            "}\n"
+            : "=f"(g), "=r"(o)
+            : "f"(s0), "f"(p0), "f"(w));
+        if (ok) *ok = o;
+        return g;
+    }
     const float2 sd = smc_add2(c.d01, make_float2(r.c0.z, r.c0.w));
     const float2 pm = smc_mul2(c.t01, make_float2(r.c0.x, r.c0.y));
     const float sz = __fadd_rn(c.dz, r.c1.y);
     const float pz = __fmul_rn(c.tz, r.c1.x);
-    float g;
     if (ok) {
         asm("{\n"
             ".reg .pred p;\n"
@@ -160,22 +174,29 @@ __device__ __forceinline__ float sym_gate(const SmcCentre<3, NG> &c, const SmcRe
 
 // One pair evaluation, booked both ways (forward to the centre, mirror to the record).  A rejected pair takes part with
 // weight 0 (one select) instead of predicating the four accumulations.
-template <int NG, bool COUNT>
-__device__ __forceinline__ void pair_sym(SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+template <int C, int NG, bool COUNT>
+__device__ __forceinline__ void pair_sym(SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
     int ok = 0;
-    const float w = sym_gate<NG>(s.c, r, sym_weight<NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
-    const float2 ww = make_float2(w, w);  // folded by ptxas into the scalar-broadcast operand form of FFMA2
-    s.n01 = smc_fma2(ww, make_float2(r.c2.x, r.c2.y), s.n01);
-    if (NG <= 6) {
-        s.n2d = smc_fma2(ww, make_float2(r.c1.z, r.c1.w), s.n2d);  // record slot 7 == 1.0f: den += w * 1
-        m.m2d = smc_fma2(ww, s.v2o, m.m2d);
-    } else {
-        s.n2d.x = __fmaf_rn(w, r.c1.z, s.n2d.x);
+    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
+    if (C == 1) {  // scalar statistics: value in record slot 4; sums (num, -, -, den)
+        s.n01.x = __fmaf_rn(w, r.c1.x, s.n01.x);
         s.n2d.y = __fadd_rn(s.n2d.y, w);
-        m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+        m.m01.x = __fmaf_rn(w, s.v01.x, m.m01.x);
         m.m2d.y = __fadd_rn(m.m2d.y, w);
+    } else {
+        const float2 ww = make_float2(w, w);  // folded by ptxas into the scalar-broadcast operand form of FFMA2
+        s.n01 = smc_fma2(ww, make_float2(r.c2.x, r.c2.y), s.n01);
+        if (NG <= 6) {
+            s.n2d = smc_fma2(ww, make_float2(r.c1.z, r.c1.w), s.n2d);  // record slot 7 == 1.0f: den += w * 1
+            m.m2d = smc_fma2(ww, s.v2o, m.m2d);
+        } else {
+            s.n2d.x = __fmaf_rn(w, r.c1.z, s.n2d.x);
+            s.n2d.y = __fadd_rn(s.n2d.y, w);
+            m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+            m.m2d.y = __fadd_rn(m.m2d.y, w);
+        }
+        m.m01 = smc_fma2(ww, s.v01, m.m01);
     }
-    m.m01 = smc_fma2(ww, s.v01, m.m01);
     if (COUNT) {
         // a tap outside the disc has -sw = +inf -> w = 0: it adds nothing, but must not be counted
         const int one = (ok && nsw.x != INFINITY) ? 1 : 0;
@@ -185,17 +206,22 @@ __device__ __forceinline__ void pair_sym(SymCentre<3, NG> &s, const SmcRec &r, f
 }
 
 // The two forward offsets that are taps of the record's window only: booked to the record.
-template <int NG, bool COUNT>
-__device__ __forceinline__ void pair_mirror_only(const SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+template <int C, int NG, bool COUNT>
+__device__ __forceinline__ void pair_mirror_only(const SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
     int ok = 0;
-    const float w = sym_gate<NG>(s.c, r, sym_weight<NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
-    const float2 ww = make_float2(w, w);
-    m.m01 = smc_fma2(ww, s.v01, m.m01);
-    if (NG <= 6) {
-        m.m2d = smc_fma2(ww, s.v2o, m.m2d);
-    } else {
-        m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
+    if (C == 1) {
+        m.m01.x = __fmaf_rn(w, s.v01.x, m.m01.x);
         m.m2d.y = __fadd_rn(m.m2d.y, w);
+    } else {
+        const float2 ww = make_float2(w, w);
+        m.m01 = smc_fma2(ww, s.v01, m.m01);
+        if (NG <= 6) {
+            m.m2d = smc_fma2(ww, s.v2o, m.m2d);
+        } else {
+            m.m2d.x = __fmaf_rn(w, s.v2o.x, m.m2d.x);
+            m.m2d.y = __fadd_rn(m.m2d.y, w);
+        }
     }
     if (COUNT) m.cnt += ok ? 1 : 0;
 }
@@ -248,8 +274,8 @@ __device__ __forceinline__ void sym_unit_start(SymTile &t, int u, const SmcFilte
 }
 
 // One record row (already in the warp's ring slot, its mirror buffer loaded) against the warp's 2 x 2 centres per lane.
-template <int NG, bool COUNT>
-__device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<3, NG> (&cen)[2][2],
+template <int C, int NG, bool COUNT>
+__device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<C, NG> (&cen)[2][2],
                                         const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,
                                         int *mcnt, int i, int base_idx) {
     const int r = p.radius;
@@ -291,14 +317,14 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
             const float2 a0 = swp0[0], a1 = swp1[0], b0 = swp0[1], b1 = swp1[1];
             sym_order();
             Mir ma = load_m(mp0, cp0), mb = load_m(mp1, cp1);
-            pair_sym<NG, COUNT>(cen[0][0], cur, a0, ma);
-            pair_sym<NG, COUNT>(cen[0][0], nxt, b0, mb);
-            pair_sym<NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
-            pair_sym<NG, COUNT>(cen[0][1], nxt, a0, mb);
-            pair_sym<NG, COUNT>(cen[1][0], cur, a1, ma);
-            pair_sym<NG, COUNT>(cen[1][0], nxt, b1, mb);
-            pair_sym<NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
-            pair_sym<NG, COUNT>(cen[1][1], nxt, a1, mb);
+            pair_sym<C, NG, COUNT>(cen[0][0], cur, a0, ma);
+            pair_sym<C, NG, COUNT>(cen[0][0], nxt, b0, mb);
+            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
+            pair_sym<C, NG, COUNT>(cen[0][1], nxt, a0, mb);
+            pair_sym<C, NG, COUNT>(cen[1][0], cur, a1, ma);
+            pair_sym<C, NG, COUNT>(cen[1][0], nxt, b1, mb);
+            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
+            pair_sym<C, NG, COUNT>(cen[1][1], nxt, a1, mb);
             store_m(mp0, cp0, ma);
             store_m(mp1, cp1, mb);
             sym_order();
@@ -312,16 +338,16 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
         if (j <= hi) {
             sym_order();
             Mir ma = load_m(mp0, cp0);
-            pair_sym<NG, COUNT>(cen[0][0], cur, swp0[0], ma);
-            pair_sym<NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
-            pair_sym<NG, COUNT>(cen[1][0], cur, swp1[0], ma);
-            pair_sym<NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
+            pair_sym<C, NG, COUNT>(cen[0][0], cur, swp0[0], ma);
+            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
+            pair_sym<C, NG, COUNT>(cen[1][0], cur, swp1[0], ma);
+            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
             store_m(mp0, cp0, ma);
             sym_order();
         }
     }
     // the two offsets booked to the record only: (0, r) in the centre's own row, (r, 0) r rows below
-    auto special = [&](const SymCentre<3, NG> &s0, const SymCentre<3, NG> &s1, int dxs) {
+    auto special = [&](const SymCentre<C, NG> &s0, const SymCentre<C, NG> &s1, int dxs) {
         const float2 nsw = make_float2(-g.sw_special, 0.f);
 #pragma unroll
         for (int kx = 0; kx < 2; kx++) {
@@ -335,7 +361,7 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
             m.m01 = make_float2(mv.x, mv.y);
             m.m2d = make_float2(mv.z, mv.w);
             m.cnt = COUNT ? *cp : 0;
-            pair_mirror_only<NG, COUNT>(kx ? s1 : s0, rec, nsw, m);
+            pair_mirror_only<C, NG, COUNT>(kx ? s1 : s0, rec, nsw, m);
             *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
             if (COUNT) *cp = m.cnt;
         }
@@ -346,7 +372,7 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
     if (i == r + 1) special(cen[1][0], cen[1][1], 0);
 }
 
-template <int NG, bool COUNT>
+template <int C, int NG, bool COUNT>
 __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFilterParams p, const SmcSymParams g) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [per warp: 2 record slots | 2 x 2 spatial-table rows | 3 mirror buffers (| 3 count buffers)] ... [rowrange]
@@ -436,7 +462,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
         const int xf = ti.x0 + 2 * lane;  // first of this lane's two centre columns
         const int base_idx = xf + p.padX - ((ti.x0 + p.padX - r) & ~1);  // slot index of the record at dx = 0, column kx = 0
 
-        SymCentre<3, NG> cen[2][2];
+        SymCentre<C, NG> cen[2][2];
         bool real[2][2];
 #pragma unroll
         for (int ky = 0; ky < 2; ky++)
@@ -446,12 +472,13 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                 // virtual positions (replicated borders, rows of other bands) carry the padded array's record
                 const int pcol = min(xc + p.padX, p.rec_pitch - 1);
                 const SmcRec rc = ldg_rec(img + (size_t)(yc + r) * row_bytes, pcol);
-                SymCentre<3, NG> &s = cen[ky][kx];
-                smc_make_centre<3, NG, 0>(rc, s.c);
-                s.v01 = make_float2(rc.c2.x, rc.c2.y);
-                // (V.z, 1): slot 7 of the record holds 1.0f when it is not the seventh G channel -- taken from the record so
-                // that the pair sits in adjacent registers as loaded (a literal 1.f would be rebuilt with moves at every use)
-                s.v2o = make_float2(rc.c1.z, NG <= 6 ? rc.c1.w : 1.f);
+                SymCentre<C, NG> &s = cen[ky][kx];
+                smc_make_centre<C, NG, 0>(rc, s.c);
+                // RGB: (V.x, V.y) and (V.z, 1) -- slot 7 of the record holds 1.0f when it is not the seventh G channel; taken
+                // from the record so that the pair sits in adjacent registers as loaded (a literal 1.f would be rebuilt with
+                // moves at every use).  Scalar statistics: the value is record slot 4.
+                s.v01 = C == 3 ? make_float2(rc.c2.x, rc.c2.y) : make_float2(rc.c1.x, 0.f);
+                s.v2o = C == 3 ? make_float2(rc.c1.z, NG <= 6 ? rc.c1.w : 1.f) : make_float2(0.f, 1.f);
                 real[ky][kx] = yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W;
                 // the centre tap: weight 1 unconditionally (is_center, stat_denoiser.cu:78, :318-323)
                 s.n01 = real[ky][kx] ? s.v01 : make_float2(0.f, 0.f);
@@ -477,7 +504,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                     : "memory");
             }
             __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
-            sym_row<NG, COUNT>(p, g, cen, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
+            sym_row<C, NG, COUNT>(p, g, cen, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
                                (float4 *)((unsigned char *)macc0 + (size_t)b * macc_bytes),
                                (int *)((unsigned char *)mcnt0 + (size_t)b * cnt_bytes), i, base_idx);
             // every lane has read the slot and written its mirror sums, which the async proxy (the bulk store) reads next
@@ -531,7 +558,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
 #pragma unroll
             for (int kx = 0; kx < 2; kx++)
                 if (real[ky][kx]) {
-                    const SymCentre<3, NG> &s = cen[ky][kx];
+                    const SymCentre<C, NG> &s = cen[ky][kx];
                     const size_t o = ((size_t)ti.z * rows_out + (ti.y0 + ky - p.row_begin)) * p.W + (xf + kx);
                     g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.n2d.x, s.n2d.y);
                     if (COUNT) g.fwd_cnt[o] = s.cnt;
@@ -548,7 +575,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
 }
 
 // out(y, x) = (forward sums + every partial mirror sum that covers the pixel) / den   (stat_denoiser.cu:341-344)
-template <bool COUNT>
+template <int C, bool COUNT>
 __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p, const SmcSymParams g) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = p.row_begin + blockIdx.y;
@@ -577,22 +604,27 @@ __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p
             if (COUNT) cnt += __ldg(g.scratch_cnt + q);
         }
     }
-    const SmcPtrStepSz ob = (p.denoise_film && z == 0) ? p.film_filtered : p.out_ptrs[z];
-    float *op = (float *)(ob.data + (size_t)y * ob.step) + x * 3;
-    op[0] = __fdiv_rn(s.x, s.w);
-    op[1] = __fdiv_rn(s.y, s.w);
-    op[2] = __fdiv_rn(s.z, s.w);
+    if (C == 3) {
+        const SmcPtrStepSz ob = (p.denoise_film && z == 0) ? p.film_filtered : p.out_ptrs[z];
+        float *op = (float *)(ob.data + (size_t)y * ob.step) + x * 3;
+        op[0] = __fdiv_rn(s.x, s.w);
+        op[1] = __fdiv_rn(s.y, s.w);
+        op[2] = __fdiv_rn(s.z, s.w);
+    } else {  // scalar statistics (stat_denoiser.cu:263-273; the plan has no film to filter along: denoise_film == 0)
+        const SmcPtrStepSz ob = p.out_ptrs[z];
+        ((float *)(ob.data + (size_t)y * ob.step))[x] = __fdiv_rn(s.x, s.w);
+    }
     if (COUNT && p.accepted && p.accepted[z].data) ((int *)(p.accepted[z].data + (size_t)y * p.accepted[z].step))[x] = cnt;
 }
 
-template <int NG>
+template <int C, int NG>
 int launch_sym_ng(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, int grid) {
     if (p.accepted != nullptr) {
-        auto k = filter_sym_kernel<NG, true>;
+        auto k = filter_sym_kernel<C, NG, true>;
         SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
     } else {
-        auto k = filter_sym_kernel<NG, false>;
+        auto k = filter_sym_kernel<C, NG, false>;
         SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
     }
@@ -600,11 +632,27 @@ int launch_sym_ng(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams
     return SMC_OK;
 }
 
+template <int C>
+int launch_sym_c(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, int grid) {
+    switch (p.NG) {
+        case 0: return launch_sym_ng<C, 0>(ctx, p, g, smem, grid);
+        case 1: return launch_sym_ng<C, 1>(ctx, p, g, smem, grid);
+        case 2: return launch_sym_ng<C, 2>(ctx, p, g, smem, grid);
+        case 3: return launch_sym_ng<C, 3>(ctx, p, g, smem, grid);
+        case 4: return launch_sym_ng<C, 4>(ctx, p, g, smem, grid);
+        case 5: return launch_sym_ng<C, 5>(ctx, p, g, smem, grid);
+        case 6: return launch_sym_ng<C, 6>(ctx, p, g, smem, grid);
+        default: return launch_sym_ng<C, 7>(ctx, p, g, smem, grid);
+    }
+}
+
 }  // namespace
 
 // ---- host side: geometry -----------------------------------------------------------------------------------------------
 bool smc_filter_sym_supported(const SmcFilterParams &p) {
-    if (p.C != 3 || p.mode != SMC_MEMBER_WELCH) return false;  // the Moon test is not symmetric (stat_denoiser.cu:132-143)
+    if (p.mode != SMC_MEMBER_WELCH) return false;  // the Moon test is not symmetric (stat_denoiser.cu:132-143)
+    // scalar statistics: unless image 0 also filters the RGB film (five sums per tap: the one-sided per-warp kernel does that)
+    if (!(p.C == 3 || (p.C == 1 && !p.denoise_film))) return false;
     if (p.radius < 2 || p.radius > SMC_MAX_RADIUS) return false;
     if (p.NG < 0 || p.NG > 7 || p.NGX > 0) return false;
     if ((p.padX & 1) || (p.rec_pitch & 1)) return false;
@@ -667,25 +715,20 @@ int smc_launch_filter_sym(smc_context *ctx, const SmcFilterParams &p, const SmcS
     const int rows = p.row_end - p.row_begin;
     if (rows <= 0) return SMC_OK;
     static thread_local char nm[80];
-    snprintf(nm, sizeof(nm), "sym-warp<NG=%d,PY=2,welch,W=%d,U=%d/%d>", p.NG, g.nwarps, g.u_big, g.u_small);
+    snprintf(nm, sizeof(nm), "sym-warp<%sNG=%d,PY=2,welch,W=%d,U=%d/%d>", p.C == 1 ? "C=1," : "", p.NG, g.nwarps, g.u_big, g.u_small);
     if (name) *name = nm;
     const int grid = (int)std::min<long long>((g.units_total + g.nwarps - 1) / g.nwarps, (long long)ctx->sm_count);
     SMC_CUDA(cudaMemsetAsync(g.unit_counter, 0, sizeof(int), ctx->stream));
-    int rc;
-    switch (p.NG) {
-        case 0: rc = launch_sym_ng<0>(ctx, p, g, smem, grid); break;
-        case 1: rc = launch_sym_ng<1>(ctx, p, g, smem, grid); break;
-        case 2: rc = launch_sym_ng<2>(ctx, p, g, smem, grid); break;
-        case 3: rc = launch_sym_ng<3>(ctx, p, g, smem, grid); break;
-        case 4: rc = launch_sym_ng<4>(ctx, p, g, smem, grid); break;
-        case 5: rc = launch_sym_ng<5>(ctx, p, g, smem, grid); break;
-        case 6: rc = launch_sym_ng<6>(ctx, p, g, smem, grid); break;
-        default: rc = launch_sym_ng<7>(ctx, p, g, smem, grid); break;
-    }
+    const int rc = p.C == 3 ? launch_sym_c<3>(ctx, p, g, smem, grid) : launch_sym_c<1>(ctx, p, g, smem, grid);
     if (rc) return rc;
     const dim3 gb(128), gg((p.W + 127) / 128, rows, p.ptr_count);
-    if (p.accepted != nullptr) sym_gather_kernel<true><<<gg, gb, 0, ctx->stream>>>(p, g);
-    else sym_gather_kernel<false><<<gg, gb, 0, ctx->stream>>>(p, g);
+    if (p.C == 3) {
+        if (p.accepted != nullptr) sym_gather_kernel<3, true><<<gg, gb, 0, ctx->stream>>>(p, g);
+        else sym_gather_kernel<3, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+    } else {
+        if (p.accepted != nullptr) sym_gather_kernel<1, true><<<gg, gb, 0, ctx->stream>>>(p, g);
+        else sym_gather_kernel<1, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+    }
     SMC_CHECK_LAUNCH(ctx);
     return SMC_OK;
 }

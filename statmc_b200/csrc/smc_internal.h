@@ -83,6 +83,7 @@ struct smc_context {
     double alpha = 0.005;
     float h_lut[SMC_T_LUT_ENTRIES];
     float *d_lut = nullptr;  // device copy of the active table
+    unsigned long long *d_accum_fallback = nullptr;  // samples the accumulate kernel redid on its scalar IEEE path
     // scratch plan cached for smc_filter_device_tables
     // (one slot per element type: Estimator::Denoise calls filter<float> and filter<float3> back to back when both
     // groups are populated, estimator.cpp:434-488, and neither plan should evict the other)

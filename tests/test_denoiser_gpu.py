@@ -238,6 +238,18 @@ def test_scalar_stream_matches_generic(ctx, W, H, r, names, membership):
         assert bits_equal(res[1][0], res[2][0])
         if denoise_film:
             assert bits_equal(res[1][1], res[2][1])
+        elif membership == 0 and r >= 2:
+            # scalar statistics without a film to filter along (the ACRR / SMIS planes): the symmetric kernel
+            out = Buffer(ctx, H, W, 1)
+            dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=-0.5 / (r / 2.0) ** 2, n=[n], mean=[dev["mean"]],
+                          m2=[dev["m2"]], m3=[dev["m3"]], film_ptrs=[val], gbufs=g, gbuf_dr_factors=f, film_filtered_ptrs=[out],
+                          denoise_film=False, kernel=0)
+            dn.run()
+            ctx.synchronize()
+            assert "sym-warp<C=1" in dn.kernel_name, dn.kernel_name
+            ok = b["n"] >= 2
+            assert rel_mad(out.download()[ok], res[2][0][ok]) <= 1e-6
+            dn.close()
     if membership == 0:
         mc, dc = po.prepass(b["n"], lum(b["mean"]), lum(b["m2"]), lum(b["m3"]))
         ref = po.filter(lum(b["film"]), [b[k] for k in names], f, r, -0.5 / (r / 2.0) ** 2, mean_corr=mc, disc=dc, precision="f64")
@@ -255,11 +267,11 @@ def test_multi_image_rgb_routing(ctx):
     outs = [Buffer(ctx, H, W, 3), Buffer(ctx, H, W, 3)]
     film, film_f = up(b0["film"]), Buffer(ctx, H, W, 3)
     g = [up(b0["normal"]), up(b0["albedo"])]
-    f = [-0.5 / 0.1 ** 2, -0.5 / 0.02 ** 2]
-    for kernel in (1, 2):
+    f = [po.f32_factor(0.1), po.f32_factor(0.02)]
+    for kernel in (1, 2, 3):
         for o in outs:
             o.zero()
-        dn = Denoiser(ctx, channels=3, width=W, height=H, radius=r, ds_factor=-0.5 / sd ** 2,
+        dn = Denoiser(ctx, channels=3, width=W, height=H, radius=r, ds_factor=po.f32_factor(sd),
                       n=[d["n"] for d in dev], mean=[d["mean"] for d in dev], m2=[d["m2"] for d in dev],
                       m3=[d["m3"] for d in dev], film_ptrs=film_mean, film=film, gbufs=g, gbuf_dr_factors=f,
                       film_filtered_ptrs=outs, film_filtered=film_f, denoise_film=True, kernel=kernel)
@@ -269,7 +281,7 @@ def test_multi_image_rgb_routing(ctx):
         e0 = po.denoise(b0, radius=r, sd=sd, precision="f64")
         assert rel_mad(film_f.download(), e0) <= TOL
         mc, dc = po.prepass(b1["n"], b1["mean"], b1["m2"], b1["m3"])
-        e1 = po.filter(b1["film"], [b0["normal"], b0["albedo"]], f, r, -0.5 / sd ** 2, mean_corr=mc, disc=dc,
+        e1 = po.filter(b1["film"], [b0["normal"], b0["albedo"]], f, r, po.f32_factor(sd), mean_corr=mc, disc=dc,
                        precision="f64")
         assert rel_mad(outs[1].download(), e1) <= TOL
         dn.close()

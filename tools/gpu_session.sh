@@ -2,7 +2,7 @@
 # scratch driver for one gpurun call: ./tools/gpu_session.sh <stage ...>; logs under gpurun_out/
 mkdir -p gpurun_out
 P='import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print("%7.1f Mpix/s step %.3f ms filter %.3f ms prepass %.3f ms  %s  parity=%s  e2e=%s" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline_prepass"]["kernel_ms"], d["config"]["kernel"], json.dumps(d.get("parity") and {k: d["parity"][k] for k in ("rel_mad","flips","ok","timed_plan_bit_identical")}), d.get("e2e") and round(d["e2e"]["value"],1)))'
-QB="python bench.py --no-cpu-baseline --no-accum --no-8k"
+QB="python bench.py --no-cpu-baseline --no-accum --no-8k --no-acrr"
 for stage in "$@"; do
   echo "=== $stage"
   case $stage in
