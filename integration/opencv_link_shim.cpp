@@ -533,6 +533,31 @@ void Stream::waitForCompletion() { check(smc_synchronize(impl_->ctx), "Stream::w
 void *Stream::cudaPtr() const { return smc_context_stream(impl_->ctx); }
 
 // ---- the denoiser -----------------------------------------------------------------------------------------------------
+#ifdef SMC_SHIM_REF_KERNELS
+}  // namespace cuda
+}  // namespace cv
+// Measurement variant (oracle/Makefile target _ref/pbrt_ref_refkernels): the Estimator still allocates and copies through
+// libstatmc_b200, but stat_denoiser::filter<T> runs the REFERENCE'S OWN kernels (stat_denoiser.cu compiled unmodified,
+// oracle/_ref/stat_denoiser.o), so that the reference's "CUDA time [ns]" line times its kernels and ours on the same data,
+// through the same Upload / Denoise / Download / Synchronize sequence.
+struct CUstream_st;
+namespace cv { namespace cuda { namespace device { namespace imgproc { namespace stat_denoiser {
+template <typename T>
+void filter(const unsigned short ptrCount, const unsigned short width, const unsigned short height, const float dSFactor,
+            const unsigned char radius, const bool denoiseFilm, const PtrStepSzb &nPtrs, const PtrStepSzb &meanPtrs,
+            const PtrStepSzb &m2Ptrs, const PtrStepSzb &m3Ptrs, const PtrStepSzb &filmPtrs, const PtrStepSzb &film,
+            const PtrStepSzb &gBufPtrs, const PtrStepSzb &gBufChannelCounts, const PtrStepSzb &gBufDRFactors,
+            const unsigned char nGBufs, PtrStepSzb meanCorrPtrs, PtrStepSzb discriminatorPtrs, PtrStepSzb filmFilteredPtrs,
+            PtrStepSzb filmFiltered, CUstream_st *stream);
+}}}}}
+namespace cv {
+void error(int code, const std::string &err, const char *func, const char *file, int line) {
+    std::fprintf(stderr, "[statmc ref kernels] cv::error %d: %s in %s (%s:%d)\n", code, err.c_str(), func, file, line);
+    std::abort();
+}
+namespace cuda {
+#endif
+
 namespace stat_denoiser {
 
 namespace {
@@ -569,6 +594,13 @@ void filter(const unsigned short ptrCount, const unsigned short width, const uns
             const unsigned char nGBufs, PtrStepSzb meanCorrPtrs, PtrStepSzb discriminatorPtrs, PtrStepSzb filmFilteredPtrs,
             PtrStepSzb filmFiltered, Stream &) {
     Shim &s = shim();
+#ifdef SMC_SHIM_REF_KERNELS
+    device::imgproc::stat_denoiser::filter<T>(ptrCount, width, height, dSFactor, radius, denoiseFilm, nPtrs, meanPtrs, m2Ptrs,
+                                              m3Ptrs, filmPtrs, film, gBufferPtrs, gBufferChannelCounts, gBufferDRFactors, nGBufs,
+                                              meanCorrPtrs, discriminatorPtrs, filmFilteredPtrs, filmFiltered,
+                                              (CUstream_st *)smc_context_stream(s.ctx));
+    return;
+#endif
     check(smc_filter_device_tables(s.ctx, ChannelsOf<T>::value, ptrCount, width, height, dSFactor, radius, denoiseFilm,
                                    nPtrs.data, meanPtrs.data, m2Ptrs.data, m3Ptrs.data, filmPtrs.data, film.data, film.step,
                                    gBufferPtrs.data, gBufferChannelCounts.data, gBufferDRFactors.data, nGBufs, meanCorrPtrs.data,

@@ -16,9 +16,10 @@
 //           copies (as smc_filter_stream.cu), one row ahead;
 //   mirror sums of a streamed row live in a shared-memory row buffer (x, y, z, den per record), read-modify-written by the
 //           lane that evaluates the pair (lanes of one instruction touch distinct records; the even / odd records of a row sit
-//           in separate arrays so that the LDS.128 / STS.128 of a warp are conflict-free).  The buffer of a row is LOADED by TMA
-//           together with the row's records (previous partial sums of the same row, or zeros on first touch) and STORED by TMA
-//           when the row is done, into a scratch array private to the work unit: no atomics, a fixed order of summation;
+//           in separate arrays so that the LDS.128 / STS.128 of a warp are conflict-free).  When the row is done its buffer is
+//           flushed -- added to the partial sums the same unit left for that row one tile earlier, or stored on first touch --
+//           into a scratch array private to the work unit, by the lanes themselves (each entry always by the same lane): no
+//           atomics, a fixed order of summation;
 //   unit  = a run of vertically adjacent tiles of one 64-column strip, processed top to bottom by one warp (units come off a
 //           global atomic counter).  Only rows at unit seams and strip seams end up with more than one partial sum;
 //   gather kernel: out(y, x) = (forward sums + the <= ~6 partial mirror sums that cover the pixel) / den.
@@ -37,7 +38,7 @@ namespace {
 
 constexpr int kTW = 64;        // centre columns per tile
 #ifndef SMC_SYM_WARPS
-#define SMC_SYM_WARPS 10       // warps per CTA the register allocation is bounded for (A/B knob)
+#define SMC_SYM_WARPS 12       // warps per CTA the register allocation is bounded for (A/B knob)
 #endif
 constexpr int kSymMaxWarps = SMC_SYM_WARPS;
 constexpr int kSymThreads = kSymMaxWarps * 32;
@@ -174,10 +175,18 @@ __device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRe
 
 // One pair evaluation, booked both ways (forward to the centre, mirror to the record).  A rejected pair takes part with
 // weight 0 (one select) instead of predicating the four accumulations.
+#ifndef SMC_SYM_GATE
+#define SMC_SYM_GATE 1  // 1: sym_gate() (weight next to the test); 0: `ok ? weight(...) : 0` (weight predicated on the test)
+#endif
 template <int C, int NG, bool COUNT>
 __device__ __forceinline__ void pair_sym(SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+#if SMC_SYM_GATE
     int ok = 0;
     const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
+#else
+    const bool ok = smc_member<C, NG, 0>(s.c, r);
+    const float w = ok ? sym_weight<C, NG>(s.c, r, nsw) : 0.f;
+#endif
     if (C == 1) {  // scalar statistics: value in record slot 4; sums (num, -, -, den)
         s.n01.x = __fmaf_rn(w, r.c1.x, s.n01.x);
         s.n2d.y = __fadd_rn(s.n2d.y, w);
@@ -375,15 +384,15 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
 template <int C, int NG, bool COUNT>
 __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFilterParams p, const SmcSymParams g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [per warp: 2 record slots | 2 x 2 spatial-table rows | 3 mirror buffers (| 3 count buffers)] ... [rowrange]
+    // layout: [per warp: 2 record slots | 2 x 2 spatial-table rows | mirror buffer (| count buffer)] ... [rowrange]
     //         [barriers: nwarps x 2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wbase = smem + (size_t)warp * g.warp_bytes;
     unsigned char *ring = wbase;
     const uint32_t sw_bytes = 2u * (uint32_t)g.sw_stride * 8u;  // two table rows of (-sw, 0) pairs
     unsigned char *swb0 = wbase + 2 * (size_t)g.slot_bytes;
-    float4 *macc0 = (float4 *)(swb0 + 2 * (size_t)sw_bytes);
-    int *mcnt0 = (int *)((unsigned char *)macc0 + 3 * (size_t)g.macc_bytes);
+    float4 *macc = (float4 *)(swb0 + 2 * (size_t)sw_bytes);
+    int *mcnt = (int *)((unsigned char *)macc + (size_t)g.macc_bytes);
     int2 *rowrange = (int2 *)(smem + (size_t)g.nwarps * g.warp_bytes);
     uint64_t *full = (uint64_t *)(rowrange + g.sw_rows) + 2 * warp;
 
@@ -406,23 +415,19 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
     const int total_warps = (int)gridDim.x * g.nwarps;
     const int rows_out = p.row_end - p.row_begin;
     // warps that run side by side start on neighbouring strips of the same unit row: the record rows they share come out of L2
-    int u_cur = (int)blockIdx.x * g.nwarps + warp;
-    if (u_cur >= g.units_total) return;
+    const int u_first = (int)blockIdx.x * g.nwarps + warp;
+    if (u_first >= g.units_total) return;
     SymTile ti;
-    sym_unit_start(ti, u_cur, p, g);
+    sym_unit_start(ti, u_first, p, g);
     const uint32_t full0 = smem_u32(&full[0]);
-    const uint32_t ring0 = smem_u32(ring), maccs = smem_u32(macc0), mcnts = smem_u32(mcnt0), sws = smem_u32(swb0);
-    const uint32_t macc_bytes = (uint32_t)g.macc_bytes, cnt_bytes = (uint32_t)g.seg_rec * 4u;
+    const uint32_t ring0 = smem_u32(ring), sws = smem_u32(swb0);
 
     // lane 0: queue the loads of stream position q = (tile t, streamed row i): the record segment and the two spatial-table
-    // rows (dy = i - 1, i) into ring slot q & 1 and the row's partial mirror sums (zeros on first touch) into mirror buffer
-    // q % 3, all completing on full[q & 1]
+    // rows (dy = i - 1, i) into ring slot q & 1, completing on full[q & 1]
     auto issue = [&](const SymTile &t, int i, uint32_t q) {
-        const uint32_t s = q & 1u, b = q % 3u;
+        const uint32_t s = q & 1u;
         const uint32_t bar = full0 + 8u * s;
-        const bool first = t.k == 0 || i >= r;  // rows r, r + 1 of a tile are new to the unit; everything is for its first tile
-        const uint32_t tx = t.bytes + sw_bytes + macc_bytes + (COUNT ? cnt_bytes : 0u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(t.bytes + sw_bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          ring0 + s * (uint32_t)g.slot_bytes),
                      "l"(t.src0 + (size_t)(i - t.i0) * row_bytes), "r"(t.bytes), "r"(bar)
@@ -431,39 +436,40 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                          sws + s * sw_bytes),
                      "l"(g.sw + (size_t)(i - 1 + g.sw_my) * g.sw_stride), "r"(sw_bytes), "r"(bar)
                      : "memory");
-        const size_t e = t.scr0 + (size_t)(t.y0 + i - t.yfirst) * g.seg_rec;
-        const void *msrc = first ? (const void *)g.zeros : (const void *)(g.scratch + e);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         maccs + b * macc_bytes),
-                     "l"(msrc), "r"(macc_bytes), "r"(bar)
-                     : "memory");
-        if (COUNT) {
-            const void *csrc = first ? (const void *)g.zeros : (const void *)(g.scratch_cnt + e);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             mcnts + b * cnt_bytes),
-                         "l"(csrc), "r"(cnt_bytes), "r"(bar)
-                         : "memory");
+    };
+    // the tile after `t` in this warp's sequence (lane 0 knows the next unit): false when the queue is empty
+    auto next_tile = [&](const SymTile &t, int u_next, SymTile &tn) {
+        if (t.k + 1 < t.nt) {
+            tn = t;
+            tn.k = t.k + 1;
+            sym_tile_place(tn, p, g);
+            return true;
         }
+        if (u_next >= g.units_total) return false;
+        sym_unit_start(tn, u_next, p, g);
+        return true;
     };
     if (lane == 0) {
         issue(ti, ti.i0, 0u);
         issue(ti, ti.i0 + 1, 1u);  // every tile streams at least two rows
     }
+    // the mirror sums of the row being streamed: zero between rows
+    for (int e = lane; e < g.seg_rec; e += 32) {
+        macc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (COUNT) mcnt[e] = 0;
+    }
 
-    uint32_t pos = 0;  // rows consumed so far: ring slot = pos & 1, phase parity = (pos >> 1) & 1, mirror buffer = pos % 3
+    uint32_t pos = 0;  // rows consumed so far: ring slot = pos & 1, phase parity = (pos >> 1) & 1
     int nxt_raw = 0;   // lane 0: the unit after the current one
     for (;;) {
         // asked for when a unit starts (~1 us), first needed two rows before the unit's last tile ends
         if (ti.k == 0 && lane == 0) nxt_raw = total_warps + atomicAdd(g.unit_counter, 1);
-        SymTile tn = ti;
-        bool have_next = false;
 
         const unsigned char *img = p.rec + (size_t)ti.z * p.rec_image_stride;
         const int xf = ti.x0 + 2 * lane;  // first of this lane's two centre columns
         const int base_idx = xf + p.padX - ((ti.x0 + p.padX - r) & ~1);  // slot index of the record at dx = 0, column kx = 0
 
         SymCentre<C, NG> cen[2][2];
-        bool real[2][2];
 #pragma unroll
         for (int ky = 0; ky < 2; ky++)
 #pragma unroll
@@ -479,16 +485,21 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                 // moves at every use).  Scalar statistics: the value is record slot 4.
                 s.v01 = C == 3 ? make_float2(rc.c2.x, rc.c2.y) : make_float2(rc.c1.x, 0.f);
                 s.v2o = C == 3 ? make_float2(rc.c1.z, NG <= 6 ? rc.c1.w : 1.f) : make_float2(0.f, 1.f);
-                real[ky][kx] = yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W;
+                const bool real = yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W;
                 // the centre tap: weight 1 unconditionally (is_center, stat_denoiser.cu:78, :318-323)
-                s.n01 = real[ky][kx] ? s.v01 : make_float2(0.f, 0.f);
-                s.n2d = real[ky][kx] ? s.v2o : make_float2(0.f, 0.f);
-                s.cnt = real[ky][kx] ? 1 : 0;
+                s.n01 = real ? s.v01 : make_float2(0.f, 0.f);
+                s.n2d = real ? s.v2o : make_float2(0.f, 0.f);
+                s.cnt = real ? 1 : 0;
             }
 
         for (int ii = 0; ii < ti.nrt; ii++, pos++) {
             const int i = ti.i0 + ii;
-            const uint32_t s = pos & 1u, b = pos % 3u;
+            const uint32_t s = pos & 1u;
+            // the unit's partial sums of this row so far (written by this lane, one tile ago): start them towards L2 now
+            const bool first = ti.k == 0 || i >= r;  // rows r, r + 1 of a tile are new to the unit; everything is for its first tile
+            float4 *sc = g.scratch + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
+            if (!first)
+                for (int e = lane; e < g.seg_rec; e += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc + e));
             {
                 const uint32_t bar = full0 + 8u * s, parity = (pos >> 1) & 1u;
                 asm volatile(
@@ -505,69 +516,61 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
             }
             __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
             sym_row<C, NG, COUNT>(p, g, cen, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
-                               (float4 *)((unsigned char *)macc0 + (size_t)b * macc_bytes),
-                               (int *)((unsigned char *)mcnt0 + (size_t)b * cnt_bytes), i, base_idx);
-            // every lane has read the slot and written its mirror sums, which the async proxy (the bulk store) reads next
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (ii == ti.nrt - 2) {  // the next tile's first row goes into this slot
-                if (ti.k + 1 < ti.nt) {
-                    tn = ti;
-                    tn.k = ti.k + 1;
-                    sym_tile_place(tn, p, g);
-                    have_next = true;
+                                  macc, mcnt, i, base_idx);
+            __syncwarp();  // every lane has read the slot and written its mirror sums
+            // Flush the row's mirror sums into the unit's scratch: plain loads and stores by the lanes.  Entry e is always
+            // handled by lane e % 32 (a strip's segments are aligned alike), so the partial sums a lane adds to are the ones it
+            // stored itself one tile earlier: program order is all the ordering this needs.
+            for (int e = lane; e < g.seg_rec; e += 32) {
+                float4 v = macc[e];
+                macc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!first) {
+                    const float4 o = __ldcg(sc + e);
+                    v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y); v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+                }
+                __stcg(sc + e, v);
+                if (COUNT) {
+                    int *scc = g.scratch_cnt + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
+                    int c = mcnt[e];
+                    mcnt[e] = 0;
+                    if (!first) c += __ldcg(scc + e);
+                    __stcg(scc + e, c);
+                }
+            }
+            if (lane == 0) {  // queue stream position pos + 2 into the slot every lane has just left
+                const int i2 = ii + 2;
+                if (i2 < ti.nrt) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(ti, ti.i0 + i2, pos + 2u);
                 } else {
-                    const int u_next = __shfl_sync(0xffffffffu, nxt_raw, 0);
-                    if (u_next < g.units_total) {
-                        sym_unit_start(tn, u_next, p, g);
-                        have_next = true;
+                    SymTile tn;
+                    if (next_tile(ti, nxt_raw, tn)) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(tn, tn.i0 + (i2 - ti.nrt), pos + 2u);
                     }
                 }
             }
-            if (lane == 0) {
-                // store this row's mirror sums to the unit's scratch
-                const size_t e = ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.scratch + e),
-                             "r"(maccs + b * macc_bytes), "r"(macc_bytes)
-                             : "memory");
-                if (COUNT)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.scratch_cnt + e),
-                                 "r"(mcnts + b * cnt_bytes), "r"(cnt_bytes)
-                                 : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // queue stream position pos + 2.  Its mirror buffer was last stored from by position pos - 1: that store
-                // must have finished READING shared memory; and if its partial sums were written by an earlier tile of this
-                // unit, that store (r - 2 positions back for full tiles) must be COMPLETE before the load is issued.
-                const int i2 = ii + 2;
-                const bool more = i2 < ti.nrt || have_next;
-                if (more) {
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    if (r >= 6 && ti.i0 == 0 && tn.i0 == 0)
-                        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-                    else
-                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                    if (i2 < ti.nrt) issue(ti, ti.i0 + i2, pos + 2u);
-                    else issue(tn, tn.i0 + (i2 - ti.nrt), pos + 2u);
-                }
-            }
+            __syncwarp();  // the zeroed mirror buffer before the next row's sums
         }
 
         // forward sums of the tile's real centres (two adjacent pixels per lane and row: 32 contiguous bytes)
 #pragma unroll
         for (int ky = 0; ky < 2; ky++)
 #pragma unroll
-            for (int kx = 0; kx < 2; kx++)
-                if (real[ky][kx]) {
+            for (int kx = 0; kx < 2; kx++) {
+                const int yc = ti.y0 + ky, xc = xf + kx;
+                if (yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W) {
                     const SymCentre<C, NG> &s = cen[ky][kx];
-                    const size_t o = ((size_t)ti.z * rows_out + (ti.y0 + ky - p.row_begin)) * p.W + (xf + kx);
+                    const size_t o = ((size_t)ti.z * rows_out + (yc - p.row_begin)) * p.W + xc;
                     g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.n2d.x, s.n2d.y);
                     if (COUNT) g.fwd_cnt[o] = s.cnt;
                 }
-        if (!have_next) break;
+            }
+        const int u_next = __shfl_sync(0xffffffffu, nxt_raw, 0);
+        SymTile tn;
+        if (!next_tile(ti, u_next, tn)) break;
         ti = tn;
     }
-    // the scratch is read by the gather kernel: every store of this warp must have landed
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }();
     // multi-GPU: when the last warp of the last CTA has read its last record, the neighbours may overwrite our halo rows
     __syncwarp();
@@ -678,7 +681,7 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     g.sw_mx = 2;
     g.sw_rows = r + 1 + 2 * g.sw_my;
     g.sw_stride = 2 * r + 2 + 2 * g.sw_mx;  // even: two table rows of 8-byte entries move as one 16-byte-aligned bulk copy
-    g.warp_bytes = 2 * g.slot_bytes + 2 * (2 * g.sw_stride * 8) + 3 * g.macc_bytes + (count ? 3 * g.seg_rec * 4 : 0);
+    g.warp_bytes = 2 * g.slot_bytes + 2 * (2 * g.sw_stride * 8) + g.macc_bytes + (count ? g.seg_rec * 4 : 0);
     g.warp_bytes = ((g.warp_bytes + 127) / 128) * 128;
     const size_t tables = (size_t)g.sw_rows * 8;
     const size_t avail = 227 * 1024 - 1024;

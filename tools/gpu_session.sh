@@ -16,6 +16,9 @@ for stage in "$@"; do
     sweep_*) # sweep_<ENVVAR>=v1:v2:...   device-resident bench per value
       kv=${stage#sweep_}; var=${kv%%=*}; vals=${kv#*=}
       for v in ${vals//:/ }; do echo -n "[$var=$v] "; env $var=$v timeout 300 $QB --no-e2e --no-parity --steps 10 2>gpurun_out/sweep.err | python -c "$P" || tail -3 gpurun_out/sweep.err; done ;;
+    accum) timeout 900 python tools/bench_accum.py --json gpurun_out/bench_accum.json 4 16 64 256 2048 2>&1 | tail -20 ;;
+    accum_quick) timeout 600 python tools/bench_accum.py --dist heavy 16 64 256 2>&1 | tail -8 ;;
+    tests_moments) timeout 900 python -m pytest tests/test_moments_gpu.py tests/test_configs_gpu.py -m gpu -x -q --timeout 600 2>&1 | tail -8 ;;
     ncu_filter) timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_sym -s 3 -c 1 -f -o gpurun_out/prof_filter $QB --no-e2e --no-parity --steps 1 --warmup 3 > gpurun_out/ncu_filter.log 2>&1; tail -2 gpurun_out/ncu_filter.log ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $QB --no-e2e --no-parity --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log ;;
     *) echo "unknown stage $stage" ;;
