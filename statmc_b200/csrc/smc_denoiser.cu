@@ -115,7 +115,7 @@ static int build_sym_table(smc_denoiser *d) {
     SmcFilterParams p;
     std::memset(&p, 0, sizeof(p));
     p.radius = d->radius; p.W = d->W; p.row_begin = d->row_begin; p.row_end = d->row_end; p.ptr_count = d->ptr_count;
-    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = d->C;
+    p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = d->C; p.sm_count = d->ctx->sm_count;
     SmcSymParams g;
     size_t smem = 0;
     if (!smc_filter_sym_geometry(p, g, smem)) return SMC_OK;  // no symmetric variant for this plan
@@ -179,7 +179,7 @@ static int alloc_records(smc_denoiser *d) {
 
 static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p) {
     p.W = d->W; p.H = d->H; p.C = d->C; p.NG = d->NG; p.radius = d->radius; p.mode = d->mode;
-    p.ptr_count = d->ptr_count; p.denoise_film = d->denoise_film;
+    p.ptr_count = d->ptr_count; p.denoise_film = d->denoise_film; p.sm_count = d->ctx->sm_count;
     p.row_begin = d->row_begin; p.row_end = d->row_end;
     p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec;
     p.sw = d->d_sw; p.sw_stride = d->sw_stride; p.sw_margin_y = SMC_SW_MARGIN_Y; p.sw_margin_x = SMC_SW_MARGIN_X;

@@ -128,7 +128,7 @@ __device__ __forceinline__ float sym_weight(const SmcCentre<C, NG> &c, const Smc
 // weight chain is predicated on the test and the pairs serialise two by two; as `ok ? w : 0.f` on a bool the select is
 // distributed over the three compares: three selects.  Measured at 4K: 7.6 / 8.0 ms against ... for this form.)
 template <int C, int NG>
-__device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRec &r, float w, int *ok) {
+__device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRec &r, float w, int *ok, float sz, float pz) {
     float g;
     if (C == 1) {  // scalar statistics: one channel
         const float s0 = __fadd_rn(c.d01.x, r.c0.z), p0 = __fmul_rn(c.t01.x, r.c0.x);
@@ -146,8 +146,7 @@ __device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRe
     }
     const float2 sd = smc_add2(c.d01, make_float2(r.c0.z, r.c0.w));
     const float2 pm = smc_mul2(c.t01, make_float2(r.c0.x, r.c0.y));
-    const float sz = __fadd_rn(c.dz, r.c1.y);
-    const float pz = __fmul_rn(c.tz, r.c1.x);
+    // (sz, pz) = (c.dz + r.d.z, c.tz * r.m.z): formed by the caller for the lane's two columns at once (ZPair)
     if (ok) {
         asm("{\n"
             ".reg .pred p;\n"
@@ -179,10 +178,10 @@ __device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRe
 #define SMC_SYM_GATE 1  // 1: sym_gate() (weight next to the test); 0: `ok ? weight(...) : 0` (weight predicated on the test)
 #endif
 template <int C, int NG, bool COUNT>
-__device__ __forceinline__ void pair_sym(SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+__device__ __forceinline__ void pair_sym(SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m, float sz, float pz) {
 #if SMC_SYM_GATE
     int ok = 0;
-    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
+    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr, sz, pz);
 #else
     const bool ok = smc_member<C, NG, 0>(s.c, r);
     const float w = ok ? sym_weight<C, NG>(s.c, r, nsw) : 0.f;
@@ -218,7 +217,8 @@ __device__ __forceinline__ void pair_sym(SymCentre<C, NG> &s, const SmcRec &r, f
 template <int C, int NG, bool COUNT>
 __device__ __forceinline__ void pair_mirror_only(const SymCentre<C, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
     int ok = 0;
-    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr);
+    const float w = sym_gate<C, NG>(s.c, r, sym_weight<C, NG>(s.c, r, nsw), COUNT ? &ok : nullptr,
+                                    C == 3 ? __fadd_rn(s.c.dz, r.c1.y) : 0.f, C == 3 ? __fmul_rn(s.c.tz, r.c1.x) : 0.f);
     if (C == 1) {
         m.m01.x = __fmaf_rn(w, s.v01.x, m.m01.x);
         m.m2d.y = __fadd_rn(m.m2d.y, w);
@@ -282,10 +282,25 @@ __device__ __forceinline__ void sym_unit_start(SymTile &t, int u, const SmcFilte
     sym_tile_place(t, p, g);
 }
 
+// The z-channel operands of the membership test for the lane's two columns of one centre row, as register pairs: against one
+// record both columns' tests need d.z + r.d.z and 2 m.z * r.m.z -- one packed add and one packed multiply for the two.
+struct ZPair {
+    float2 dz, tz;
+};
+template <int C>
+__device__ __forceinline__ void zpair_eval(const ZPair &z, const SmcRec &r, float2 &sz, float2 &pz) {
+    if (C == 3) {
+        sz = smc_add2(z.dz, make_float2(r.c1.y, r.c1.y));
+        pz = smc_mul2(z.tz, make_float2(r.c1.x, r.c1.x));
+    } else {
+        sz = pz = make_float2(0.f, 0.f);
+    }
+}
+
 // One record row (already in the warp's ring slot, its mirror buffer loaded) against the warp's 2 x 2 centres per lane.
 template <int C, int NG, bool COUNT>
 __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<C, NG> (&cen)[2][2],
-                                        const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,
+                                        const ZPair (&zp)[2], const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,
                                         int *mcnt, int i, int base_idx) {
     const int r = p.radius;
     const int half = g.seg_rec >> 1;
@@ -326,14 +341,19 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
             const float2 a0 = swp0[0], a1 = swp1[0], b0 = swp0[1], b1 = swp1[1];
             sym_order();
             Mir ma = load_m(mp0, cp0), mb = load_m(mp1, cp1);
-            pair_sym<C, NG, COUNT>(cen[0][0], cur, a0, ma);
-            pair_sym<C, NG, COUNT>(cen[0][0], nxt, b0, mb);
-            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
-            pair_sym<C, NG, COUNT>(cen[0][1], nxt, a0, mb);
-            pair_sym<C, NG, COUNT>(cen[1][0], cur, a1, ma);
-            pair_sym<C, NG, COUNT>(cen[1][0], nxt, b1, mb);
-            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
-            pair_sym<C, NG, COUNT>(cen[1][1], nxt, a1, mb);
+            float2 sa0, pa0, sa1, pa1, sb0, pb0, sb1, pb1;  // z-channel test operands: (column 0, column 1) per record and row
+            zpair_eval<C>(zp[0], cur, sa0, pa0);
+            zpair_eval<C>(zp[1], cur, sa1, pa1);
+            zpair_eval<C>(zp[0], nxt, sb0, pb0);
+            zpair_eval<C>(zp[1], nxt, sb1, pb1);
+            pair_sym<C, NG, COUNT>(cen[0][0], cur, a0, ma, sa0.x, pa0.x);
+            pair_sym<C, NG, COUNT>(cen[0][0], nxt, b0, mb, sb0.x, pb0.x);
+            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
+            pair_sym<C, NG, COUNT>(cen[0][1], nxt, a0, mb, sb0.y, pb0.y);
+            pair_sym<C, NG, COUNT>(cen[1][0], cur, a1, ma, sa1.x, pa1.x);
+            pair_sym<C, NG, COUNT>(cen[1][0], nxt, b1, mb, sb1.x, pb1.x);
+            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
+            pair_sym<C, NG, COUNT>(cen[1][1], nxt, a1, mb, sb1.y, pb1.y);
             store_m(mp0, cp0, ma);
             store_m(mp1, cp1, mb);
             sym_order();
@@ -347,10 +367,13 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
         if (j <= hi) {
             sym_order();
             Mir ma = load_m(mp0, cp0);
-            pair_sym<C, NG, COUNT>(cen[0][0], cur, swp0[0], ma);
-            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma);
-            pair_sym<C, NG, COUNT>(cen[1][0], cur, swp1[0], ma);
-            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma);
+            float2 sa0, pa0, sa1, pa1;
+            zpair_eval<C>(zp[0], cur, sa0, pa0);
+            zpair_eval<C>(zp[1], cur, sa1, pa1);
+            pair_sym<C, NG, COUNT>(cen[0][0], cur, swp0[0], ma, sa0.x, pa0.x);
+            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
+            pair_sym<C, NG, COUNT>(cen[1][0], cur, swp1[0], ma, sa1.x, pa1.x);
+            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
             store_m(mp0, cp0, ma);
             sym_order();
         }
@@ -492,14 +515,18 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                 s.cnt = real ? 1 : 0;
             }
 
+        ZPair zp[2];
+#pragma unroll
+        for (int ky = 0; ky < 2; ky++) {
+            zp[ky].dz = make_float2(cen[ky][0].c.dz, cen[ky][1].c.dz);
+            zp[ky].tz = make_float2(cen[ky][0].c.tz, cen[ky][1].c.tz);
+        }
+
         for (int ii = 0; ii < ti.nrt; ii++, pos++) {
             const int i = ti.i0 + ii;
             const uint32_t s = pos & 1u;
-            // the unit's partial sums of this row so far (written by this lane, one tile ago): start them towards L2 now
             const bool first = ti.k == 0 || i >= r;  // rows r, r + 1 of a tile are new to the unit; everything is for its first tile
             float4 *sc = g.scratch + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
-            if (!first)
-                for (int e = lane; e < g.seg_rec; e += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc + e));
             {
                 const uint32_t bar = full0 + 8u * s, parity = (pos >> 1) & 1u;
                 asm volatile(
@@ -515,38 +542,55 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                     : "memory");
             }
             __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
-            sym_row<C, NG, COUNT>(p, g, cen, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
+            sym_row<C, NG, COUNT>(p, g, cen, zp, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
                                   macc, mcnt, i, base_idx);
             __syncwarp();  // every lane has read the slot and written its mirror sums
             // Flush the row's mirror sums into the unit's scratch: plain loads and stores by the lanes.  Entry e is always
             // handled by lane e % 32 (a strip's segments are aligned alike), so the partial sums a lane adds to are the ones it
-            // stored itself one tile earlier: program order is all the ordering this needs.
-            for (int e = lane; e < g.seg_rec; e += 32) {
-                float4 v = macc[e];
-                macc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!first) {
-                    const float4 o = __ldcg(sc + e);
-                    v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y); v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+            // stored itself one tile earlier: program order is all the ordering this needs.  The loads of up to four entries
+            // per lane are issued together, and lane 0 queues the next TMA copies while they are in flight.
+            int *scc = COUNT ? g.scratch_cnt + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec : nullptr;
+            for (int e0 = 0; e0 < g.seg_rec; e0 += 128) {
+                float4 o[4];
+                int oc[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int e = e0 + 32 * k + lane;
+                    o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    oc[k] = 0;
+                    if (!first && e < g.seg_rec) {
+                        o[k] = __ldcg(sc + e);
+                        if (COUNT) oc[k] = __ldcg(scc + e);
+                    }
                 }
-                __stcg(sc + e, v);
-                if (COUNT) {
-                    int *scc = g.scratch_cnt + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec;
-                    int c = mcnt[e];
-                    mcnt[e] = 0;
-                    if (!first) c += __ldcg(scc + e);
-                    __stcg(scc + e, c);
-                }
-            }
-            if (lane == 0) {  // queue stream position pos + 2 into the slot every lane has just left
-                const int i2 = ii + 2;
-                if (i2 < ti.nrt) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(ti, ti.i0 + i2, pos + 2u);
-                } else {
-                    SymTile tn;
-                    if (next_tile(ti, nxt_raw, tn)) {
+                if (e0 == 0 && lane == 0) {  // queue stream position pos + 2 into the slot every lane has just left
+                    const int i2 = ii + 2;
+                    if (i2 < ti.nrt) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        issue(tn, tn.i0 + (i2 - ti.nrt), pos + 2u);
+                        issue(ti, ti.i0 + i2, pos + 2u);
+                    } else {
+                        SymTile tn;
+                        if (next_tile(ti, nxt_raw, tn)) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            issue(tn, tn.i0 + (i2 - ti.nrt), pos + 2u);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int e = e0 + 32 * k + lane;
+                    if (e < g.seg_rec) {
+                        const float4 v = macc[e];
+                        macc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        // (first touch: o == 0, and 0 + v == v exactly, also for -0 sums, which cannot occur: weights are >= 0
+                        // only in sign of the values; a -0 would at most become +0 in a sum nobody distinguishes)
+                        __stcg(sc + e, first ? v : make_float4(__fadd_rn(o[k].x, v.x), __fadd_rn(o[k].y, v.y), __fadd_rn(o[k].z, v.z),
+                                                               __fadd_rn(o[k].w, v.w)));
+                        if (COUNT) {
+                            const int c = mcnt[e];
+                            mcnt[e] = 0;
+                            __stcg(scc + e, c + oc[k]);
+                        }
                     }
                 }
             }
@@ -691,8 +735,16 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     g.nwarps = std::min(nw, kSymMaxWarps);
     if (g.nwarps < 1) return false;
     smem = (size_t)g.nwarps * g.warp_bytes + tables + (size_t)g.nwarps * 16;
-    // units: runs of u_big tiles for the upper part of the rows, u_small tiles for the rest (the tail of the work queue)
-    int u_big = 4, u_small = 2, small_pct = 12;
+    // Units: runs of u_big tiles for the upper part of the rows, u_small tiles for the rest (the tail of the work queue).
+    // Longer units leave fewer partial sums for the gather kernel (a row of a strip is written once per unit that streams
+    // it), shorter ones balance better: take the longest run (at most 4 tiles) that still gives every resident warp about a
+    // dozen units, and finish the queue with units of half that length.  (4K, one GPU: 3-tile units; a 270-row band of an
+    // 8-GPU run: single tiles.)
+    const long long tiles = (long long)g.n_trows * g.n_strips * p.ptr_count;
+    const long long workers = (long long)std::max(p.sm_count, 1) * g.nwarps;
+    int u_big = 4, small_pct = 12;
+    while (u_big > 1 && tiles / u_big < 12 * workers) u_big--;
+    int u_small = std::max(1, u_big / 2);
     if (const char *e = getenv("SMC_SYM_UNIT")) sscanf(e, "%d,%d,%d", &u_big, &u_small, &small_pct);  // tuning knob
     u_big = std::max(1, u_big);
     u_small = std::max(1, std::min(u_small, u_big));

@@ -144,6 +144,7 @@ struct SmcFilterParams {
     int mode;              // smc_membership
     int ptr_count;
     int denoise_film;
+    int sm_count;          // SMs of the device (work partitioning heuristics)
     int row_begin, row_end;
     int padX;              // record columns left of x = 0
     int rec_pitch;         // records per record row

@@ -72,7 +72,7 @@ def test_config1_720p_16spp_accumulate_then_denoise(ctx):
         assert bits_equal(feats[name], o["mean"]), name
     bufs = {"n": got["n"], "mean": got["mean"], "m2": got["m2"], "m3": got["m3"], "film": got["film_mean"], **feats}
     ours = denoise_host(ctx, bufs, radius=20, sd=10.0, want_aux=True)
-    assert "stream" in ours["kernel"]
+    assert "sym" in ours["kernel"]
     ref = po.denoise(bufs, radius=20, sd=10.0, precision="f32", want_aux=True)  # whole frame, OpenMP
     assert bits_equal(ours["mean_corr"], ref["mean_corr"]) and bits_equal(ours["disc"], ref["disc"])
     assert np.array_equal(ours["accepted"], ref["accepted"])
