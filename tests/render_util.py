@@ -23,7 +23,7 @@ Integrator "statpath"
   "bool calcitstats" ["false"]
   "float filtersd" [{sd}] "integer filterradius" [{radius}]
   "string filterbuffers" ["albedo" "normal"] "float filterbuffersds" [0.02 0.1]
-  "string outputregex" [".*"]
+  "string outputregex" ["{outputregex}"]
 Sampler "random" "integer pixelsamples" [4]
 LookAt 0 3.2 8.5  0 0.7 0  0 1 0
 Camera "perspective" "float fov" [36]
@@ -63,7 +63,7 @@ WorldEnd
 
 
 def write_scene(directory, width=96, height=64, radius=8, sd=4.0, iterations=3, trackedbounces=0, multichannelstats=True,
-                denoiseimage=True, acrr=False, smis=False, calcprodenstats=False):
+                denoiseimage=True, acrr=False, smis=False, calcprodenstats=False, outputregex=".*"):
     """scenes/render-denoise.pbrt by default; acrr.pbrt = trackedbounces 5, multichannelstats / denoiseimage false, acrr true;
     smis.pbrt = trackedbounces 6, multichannelstats / denoiseimage false, smis true; render-for-proden.pbrt = denoiseimage
     false, calcprodenstats true."""
@@ -73,7 +73,8 @@ def write_scene(directory, width=96, height=64, radius=8, sd=4.0, iterations=3, 
     with open(path, "w") as f:
         f.write(SCENE.format(width=width, height=height, radius=radius, sd=sd, iterations=iterations, stem=stem,
                              trackedbounces=trackedbounces, multichannelstats=b(multichannelstats),
-                             denoiseimage=b(denoiseimage), acrr=b(acrr), smis=b(smis), calcprodenstats=b(calcprodenstats)))
+                             denoiseimage=b(denoiseimage), acrr=b(acrr), smis=b(smis), calcprodenstats=b(calcprodenstats),
+                             outputregex=outputregex))
     return path, stem
 
 

@@ -19,6 +19,18 @@ for stage in "$@"; do
     accum) timeout 900 python tools/bench_accum.py --json gpurun_out/bench_accum.json 4 16 64 256 2048 2>&1 | tail -20 ;;
     accum_quick) timeout 600 python tools/bench_accum.py --dist heavy 16 64 256 2>&1 | tail -8 ;;
     tests_moments) timeout 900 python -m pytest tests/test_moments_gpu.py tests/test_configs_gpu.py -m gpu -x -q --timeout 600 2>&1 | tail -8 ;;
+    render) timeout 1500 python tools/bench_ref_render.py --out gpurun_out/ref_render.json 2>&1 | tail -3 | cut -c1-1500 ;;
+    probe) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 tools/probe_h2d.py --out gpurun_out/probe_h2d_n${NGPU:-2}.json 2>&1 | tail -40 ;;
+    mgpu_tests) timeout 1200 python -m pytest tests/test_multigpu_gpu.py -m gpu -x -q --timeout 900 2>&1 | tail -8 ;;
+    mgpu_bench) for n in ${NLIST:-2}; do echo "--- N=$n"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 2>gpurun_out/bench_n$n.err | tee gpurun_out/bench_n$n.json | python -c "$P" || tail -5 gpurun_out/bench_n$n.err; python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_n$n.json").read().strip().splitlines()[-1])
+k=d.get("config4_8k") or {}
+print("   8k: %s Mpix/s %s ms parity=%s" % (k.get("value"), k.get("ms_per_step"), (k.get("parity") or {}).get("ok")))
+print("   e2e: %s" % (d.get("e2e") and d["e2e"]["value"]))
+PY
+done ;;
+    pipe_trace) SMC_PIPE_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus ${NGPU:-2} --steps 3 --warmup 3 --no-8k --no-accum 2> gpurun_out/pipe_trace_n${NGPU:-2}.txt | tail -1 | cut -c1-300 ;;
     ncu_filter) timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_sym -s 3 -c 1 -f -o gpurun_out/prof_filter $QB --no-e2e --no-parity --steps 1 --warmup 3 > gpurun_out/ncu_filter.log 2>&1; tail -2 gpurun_out/ncu_filter.log ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $QB --no-e2e --no-parity --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log ;;
     *) echo "unknown stage $stage" ;;
