@@ -640,7 +640,7 @@ def main():
         sym = "sym" in main_leg["kernel"]
         # FP32-pipe lane-cycles per ORDERED pair (tap) in the SASS of the kernel that ran: the
         # symmetric kernel evaluates an unordered pair once (28 lane-cycles) and books it to both pixels
-        lane_ops = 14 if sym else 24
+        lane_ops = 13.5 if sym else 24
         fp32_ach = pairs * lane_ops / (f_ms * 1e-3)
         default_1gpu = default_run and world == 1
         cfg = workload_config(args.workload, W, H, radius, sd, n)

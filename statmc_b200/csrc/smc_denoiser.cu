@@ -583,6 +583,10 @@ static int auto_chunk_rows(const smc_denoiser *d) {
         long long k = (total / std::max(grid, 1) + 4) / 8;
         if (k < 1) k = 1;
         chunk = (int)(k * grid / tiles_x) * d->py;
+    } else if (d->use_sym) {
+        // every launch of the symmetric kernel re-evaluates the `radius` rows above its range as virtual centres (about
+        // 0.42 radius rows of work): about six chunks per frame, none shorter than four radii
+        chunk = std::max(((rows / 6 + 7) / 8) * 8, 4 * d->radius);
     } else {
         chunk = ((rows / 8 + 7) / 8) * 8;
     }

@@ -61,6 +61,7 @@ def test_estimator_cpp(tmp_path):
     ref = po.denoise(bufs, radius=r, sd=sd, precision="f64", want_aux=True, gbuf_sds=(nsd, asd))
     assert bits_equal(mc, ref["mean_corr"]) and bits_equal(dc, ref["disc"])
     assert rel_mad(film_f, ref["film_f"]) <= 1e-4
-    # replay through host planes (pipelined) and through the device-table kernel API: same bits as the first run
-    assert bits_equal(film_f2, film_f)
+    # replay through the device-table kernel API: same bits as the first run; through host planes (pipelined in row chunks):
+    # the symmetric filter may cut its sums differently
+    assert rel_mad(film_f2, film_f) <= 1e-6
     assert bits_equal(film_f3, film_f)

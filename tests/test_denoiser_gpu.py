@@ -418,3 +418,46 @@ def test_peer_halo_mode(ctx, kernel):
         assert _same_rows(got, full, kernel), step
     for dn, *_ in plans:
         dn.close()
+
+
+def test_device_table_plan_follows_table_contents(ctx):
+    # smc_filter_device_tables (the reference's argument list: device-resident PtrStepSzb tables, cudaimgproc.hpp:756-777)
+    # caches its plan; the G-buffer channel counts and range factors live in device memory and may change under the same
+    # addresses (a second Estimator on recycled allocations).  The tables are read on every call: the result must follow.
+    import ctypes as C
+    W, H, r, sd = 96, 40, 6, 3.0
+    b = small_buffers(W, H)
+    names = ("n", "mean", "m2", "m3", "film", "normal", "albedo")
+    dev = {k: Buffer.from_array(ctx, b[k]) for k in names}
+    mc, dc, dummy, out = (Buffer(ctx, H, W, 3) for _ in range(4))
+
+    def table(bufs):  # 1 x N table of {data, step, cols, rows} (cv::cuda::PtrStepSzb, 24 bytes)
+        a = np.zeros((len(bufs), 3), dtype=np.uint64)
+        for i, x in enumerate(bufs):
+            a[i] = (x.plane.dev, x.plane.step, (H << 32) | W)
+        t = Buffer(ctx, 1, len(bufs) * 6, 1, np.int32)
+        t.upload(a.view(np.int32).reshape(1, -1))
+        return t
+
+    t = {k: table([dev[k]]) for k in ("n", "mean", "m2", "m3", "film")}
+    tg, tmc, tdc, tout = table([dev["normal"], dev["albedo"]]), table([mc]), table([dc]), table([dummy])
+    gch = Buffer(ctx, 1, 4, 1, np.int32)     # uchar[2] channel counts inside an int32 plane
+    gf = Buffer(ctx, 1, 2, 1, np.float32)
+    gch.upload(np.frombuffer(bytes([3, 3, 0, 0]) + bytes(12), dtype=np.int32).reshape(1, 4))
+    dv = lambda x: C.c_void_p(capi.lib.smc_buffer_dev(x.h))
+
+    def run(normal_sd, albedo_sd):
+        gf.upload(np.array([[po.f32_factor(normal_sd), po.f32_factor(albedo_sd)]], dtype=np.float32))
+        capi.check(capi.lib.smc_filter_device_tables(
+            ctx.h, 3, 1, W, H, po.f32_factor(sd), r, 1, dv(t["n"]), dv(t["mean"]), dv(t["m2"]), dv(t["m3"]), dv(t["film"]),
+            dv(dev["film"]), dev["film"].plane.step, dv(tg), dv(gch), dv(gf), 2, dv(tmc), dv(tdc), dv(tout), dv(out),
+            out.plane.step, C.c_void_p(ctx.stream)))
+        ctx.synchronize()
+        return out.download()
+
+    for sds in ((0.1, 0.02), (0.5, 0.3), (0.1, 0.02)):  # same addresses, other factors, and back
+        got = run(*sds)
+        ref = po.denoise(b, radius=r, sd=sd, gbuf_sds=sds, precision="f64")
+        assert rel_mad(got, ref) <= TOL, sds
+    a, c = run(0.1, 0.02), run(0.5, 0.3)
+    assert rel_mad(a, c) > 1e-3  # the two settings really differ

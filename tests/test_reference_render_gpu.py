@@ -13,6 +13,7 @@ import pytest
 
 import render_util as ru
 from oracle import pyoracle as po
+from statmc_b200 import pfm
 from statmc_b200.api import denoise_host
 from util import bits_equal, max_abs, rel_mad
 
@@ -62,3 +63,25 @@ def test_reference_renderer_on_libstatmc_b200(tmp_path):
     ru.run_pbrt(ru.PBRT_B200, scene, "--denoise", "--writeimages")
     for spp in (4, 8, 16):
         assert bits_equal(ru.read_dump(stem, spp)["film_f"], first[spp]), spp
+
+
+REFK = os.path.join(os.path.dirname(ru.PBRT_B200), "pbrt_ref_refkernels")
+
+
+@pytest.mark.skipif(not (os.path.exists(ru.PBRT_B200) and os.path.exists(REFK)),
+                    reason="oracle/_ref/pbrt_ref_b200 / pbrt_ref_refkernels not built (need /root/reference)")
+def test_real_render_against_the_reference_kernels(tmp_path):
+    # Two links of the reference's renderer render the same frame (same random numbers): one denoises on libstatmc_b200, the
+    # other with the reference's own kernels on the same buffers.  Real 16-spp statistics at 640 x 360 (tools/bench_ref_render.py
+    # does the same at BASELINE configs[0]'s 1280 x 720 and records the reference's own timer).
+    out = {}
+    for tag, exe in (("ours", ru.PBRT_B200), ("refk", REFK)):
+        d = tmp_path / tag
+        d.mkdir()
+        scene, stem = ru.write_scene(d, width=640, height=360, radius=20, sd=10.0, outputregex="film|film-f")
+        ru.run_pbrt(exe, scene, "--writeimages", nthreads=os.cpu_count() or 8)
+        out[tag] = (pfm.read("%s-16-film.pfm" % stem), pfm.read("%s-16-film-f.pfm" % stem))
+    assert bits_equal(out["ours"][0], out["refk"][0]), "the two links rendered different frames"
+    rm = rel_mad(out["ours"][1], out["refk"][1])
+    print("real 640x360 16-spp render: film-f relMAD vs the reference's kernels %.2e, max-abs %.2e" % (rm, max_abs(out["ours"][1], out["refk"][1])))
+    assert rm <= 1e-4

@@ -51,11 +51,12 @@ def test_replay_rgb_default(tmp_path):
         assert bits_equal(pfm.read("%s-%d-t0-b0-mean-corr.pfm" % (out, spp)), want[spp]["mean_corr"])
         assert bits_equal(pfm.read("%s-%d-t0-b0-discriminator.pfm" % (out, spp)), want[spp]["disc"])
         assert np.all(pfm.read("%s-%d-t0-b0-n.pfm" % (out, spp), np.int32) == spp)
-    # the pipelined host path (Upload + Denoise + Download as one chunked call) writes the same bits
+    # the pipelined host path (Upload + Denoise + Download as one chunked call) runs the same kernels over row chunks: the
+    # symmetric filter then cuts its sums differently (same weights, same decisions, other order of summation)
     out2 = str(tmp_path / "res2")
     _run(*[out2 if a == out else a for a in args], "--pipelined")
     for spp in (4, 8):
-        assert bits_equal(pfm.read("%s-%d-film-f.pfm" % (out2, spp)), got[spp])
+        assert rel_mad(pfm.read("%s-%d-film-f.pfm" % (out2, spp)), got[spp]) <= 1e-6
 
 
 def test_replay_scalar_acrr_smis(tmp_path):
