@@ -39,7 +39,6 @@ struct smc_denoiser {
     float2 *d_sym_sw = nullptr;
     int2 *d_sym_rowrange = nullptr;
     float sym_sw_special = 0.f;
-    void *d_sym_zeros = nullptr;
     float4 *d_sym_scratch = nullptr, *d_sym_fwd = nullptr;
     int *d_sym_scratch_cnt = nullptr, *d_sym_fwd_cnt = nullptr;
     size_t sym_scratch_elems = 0, sym_fwd_elems = 0;
@@ -143,9 +142,6 @@ static int build_sym_table(smc_denoiser *d) {
     SMC_CUDA(cudaMalloc(&d->d_sym_rowrange, rr.size() * sizeof(int2)));
     SMC_CUDA(cudaMemcpyAsync(d->d_sym_sw, sw.data(), sw.size() * sizeof(float2), cudaMemcpyHostToDevice, d->ctx->stream));
     SMC_CUDA(cudaMemcpyAsync(d->d_sym_rowrange, rr.data(), rr.size() * sizeof(int2), cudaMemcpyHostToDevice, d->ctx->stream));
-    const size_t zb = (size_t)g.macc_bytes;
-    SMC_CUDA(cudaMalloc(&d->d_sym_zeros, zb));
-    SMC_CUDA(cudaMemsetAsync(d->d_sym_zeros, 0, zb, d->ctx->stream));
     SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));  // sources are stack/pageable
     return SMC_OK;
 }
@@ -374,7 +370,6 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     cudaFree(d->d_rowrange);
     cudaFree(d->d_sym_sw);
     cudaFree(d->d_sym_rowrange);
-    cudaFree(d->d_sym_zeros);
     cudaFree(d->d_sym_scratch);
     cudaFree(d->d_sym_scratch_cnt);
     cudaFree(d->d_sym_fwd);
@@ -468,7 +463,7 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
         }
         g.sw = d->d_sym_sw; g.rowrange = d->d_sym_rowrange; g.sw_special = d->sym_sw_special;
         g.scratch = d->d_sym_scratch; g.scratch_cnt = d->d_sym_scratch_cnt; g.fwd = d->d_sym_fwd; g.fwd_cnt = d->d_sym_fwd_cnt;
-        g.zeros = d->d_sym_zeros; g.unit_counter = d->d_tile_counter;
+        g.unit_counter = d->d_tile_counter;
         const char *nm = nullptr;
         const int rc = smc_launch_filter_sym(d->ctx, p, g, smem, &nm);
         if (nm) snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", nm);

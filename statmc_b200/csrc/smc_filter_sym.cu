@@ -126,7 +126,8 @@ __device__ __forceinline__ float sym_weight(const SmcCentre<C, NG> &c, const Smc
 // Written as one PTX block -- three chained compares and one select -- so that the weight is computed NEXT TO the test and the
 // eight pair evaluations of a loop iteration stay one straight-line block for the scheduler.  (As `ok ? weight(...) : 0.f` the
 // weight chain is predicated on the test and the pairs serialise two by two; as `ok ? w : 0.f` on a bool the select is
-// distributed over the three compares: three selects.  Measured at 4K: 7.6 / 8.0 ms against ... for this form.)
+// distributed over the three compares: three selects.  Measured at 4K with 12 warps: 7.19 ms for this form, 7.36 ms with the
+// weight predicated on the test.)
 template <int C, int NG>
 __device__ __forceinline__ float sym_gate(const SmcCentre<C, NG> &c, const SmcRec &r, float w, int *ok, float sz, float pz) {
     float g;
@@ -297,7 +298,7 @@ __device__ __forceinline__ void zpair_eval(const ZPair &z, const SmcRec &r, floa
     }
 }
 
-// One record row (already in the warp's ring slot, its mirror buffer loaded) against the warp's 2 x 2 centres per lane.
+// One record row (already in the warp's ring slot; the mirror buffer holds zeros) against the warp's 2 x 2 centres per lane.
 template <int C, int NG, bool COUNT>
 __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<C, NG> (&cen)[2][2],
                                         const ZPair (&zp)[2], const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,

@@ -184,7 +184,6 @@ struct SmcSymParams {
     int *scratch_cnt;  // same indexing: partial accepted-tap counts (only with an `accepted` plane)
     float4 *fwd;       // [image][row_end - row_begin][W]: forward sums
     int *fwd_cnt;
-    const void *zeros; // >= macc_bytes zero bytes: what a row's mirror buffer is loaded from on first touch
     int *unit_counter;
 };
 
