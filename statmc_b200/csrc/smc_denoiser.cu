@@ -641,6 +641,22 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
         bounds.push_back(H - prelast - last);
         bounds.push_back(H - last);
         bounds.push_back(H);
+    } else if (auto_chunks && d->use_sym && !(tp && atoi(tp) == 0)) {
+        // Symmetric kernel: uniform chunks while the bus is the critical path, then halving chunks.  Whatever is filtered
+        // and downloaded after the last byte has arrived is pure latency: a 360-row last chunk costs 1.2 ms + 0.5 ms at 4K, a
+        // 90-row one 0.35 ms + 0.12 ms; the extra launches run under the uploads.  (SMC_PIPE_TAPER=0: uniform chunks.)
+        const int min_chunk = std::max(2 * r + 8, 48);
+        int a = 0;
+        bounds.push_back(0);
+        while (H - a > 2 * chunk_rows) {
+            a += chunk_rows;
+            bounds.push_back(a);
+        }
+        while (H - a > 2 * min_chunk) {
+            a += (((H - a) / 2 + 7) / 8) * 8;
+            bounds.push_back(a);
+        }
+        bounds.push_back(H);
     } else {
         for (int a = 0; a < H; a += chunk_rows) bounds.push_back(a);
         if (bounds.back() < H) bounds.push_back(H);
