@@ -744,16 +744,19 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     g.nwarps = std::min(nw, kSymMaxWarps);
     if (g.nwarps < 1) return false;
     smem = (size_t)g.nwarps * g.warp_bytes + tables + (size_t)g.nwarps * 16;
-    // Units: runs of u_big tiles for the upper part of the rows, u_small tiles for the rest (the tail of the work queue).
+    // Units: runs of u_big tiles for the upper part of the rows, single tiles for the rest (the tail of the work queue).
     // Longer units leave fewer partial sums for the gather kernel (a row of a strip is written once per unit that streams
-    // it), shorter ones balance better: take the longest run (at most 4 tiles) that still gives every resident warp eight
-    // units or more, and finish the queue with units of half that length.  (4K, one GPU: 4-tile units, measured 7.19 ms
-    // against 7.35 ms with 3-tile units; a 270-row band of an 8-GPU run: single tiles.)
+    // it); single tiles balance best.  With s tiles per resident warp, every warp takes floor(s / u_big) long units off the
+    // queue and the remainder goes out tile by tile, so the makespan stays ceil(s) tiles whatever u_big <= s / 2 is: take the
+    // longest run up to 4 tiles.  (4K on one GPU: s = 37, 4-tile units and 4 % single tiles; a 270-row band of an 8-GPU run:
+    // s = 5, 2-tile units and 20 % single tiles.)
     const long long tiles = (long long)g.n_trows * g.n_strips * p.ptr_count;
     const long long workers = (long long)std::max(p.sm_count, 1) * g.nwarps;
-    int u_big = 4, small_pct = 12;
-    while (u_big > 1 && tiles / u_big < 8 * workers) u_big--;
-    int u_small = std::max(1, u_big / 2);
+    const double share = (double)tiles / (double)workers;
+    int u_big = std::max(1, std::min(4, (int)(share / 2.0)));
+    const long long big_tiles = (long long)(share / u_big) * u_big * workers;  // what the long units may cover
+    int small_pct = (int)std::min<long long>(100, std::max<long long>(3, 100 - big_tiles * 100 / std::max<long long>(tiles, 1) + 1));
+    int u_small = 1;
     if (const char *e = getenv("SMC_SYM_UNIT")) sscanf(e, "%d,%d,%d", &u_big, &u_small, &small_pct);  // tuning knob
     u_big = std::max(1, u_big);
     u_small = std::max(1, std::min(u_small, u_big));
