@@ -39,6 +39,10 @@ struct smc_denoiser {
     float2 *d_sym_sw = nullptr;
     int2 *d_sym_rowrange = nullptr;
     float sym_sw_special = 0.f;
+    // three scalar images per record (see alloc_records): the records, the prepass grid and the filter run over `rec_images`
+    // = ceil(ptr_count / 3) record images
+    int tri = 0, rec_images = 1;
+    float2 *d_sym_scratch2 = nullptr, *d_sym_fwd2 = nullptr;
     float4 *d_sym_scratch = nullptr, *d_sym_fwd = nullptr;
     int *d_sym_scratch_cnt = nullptr, *d_sym_fwd_cnt = nullptr;
     size_t sym_scratch_elems = 0, sym_fwd_elems = 0;
@@ -113,8 +117,9 @@ static int build_spatial_table(smc_denoiser *d) {
 static int build_sym_table(smc_denoiser *d) {
     SmcFilterParams p;
     std::memset(&p, 0, sizeof(p));
-    p.radius = d->radius; p.W = d->W; p.row_begin = d->row_begin; p.row_end = d->row_end; p.ptr_count = d->ptr_count;
+    p.radius = d->radius; p.W = d->W; p.row_begin = d->row_begin; p.row_end = d->row_end; p.ptr_count = d->rec_images;
     p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.C = d->C; p.sm_count = d->ctx->sm_count;
+    p.tri = d->tri; p.images = d->ptr_count;
     SmcSymParams g;
     size_t smem = 0;
     if (!smc_filter_sym_geometry(p, g, smem)) return SMC_OK;  // no symmetric variant for this plan
@@ -146,6 +151,8 @@ static int build_sym_table(smc_denoiser *d) {
     return SMC_OK;
 }
 
+static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p);
+
 static int alloc_records(smc_denoiser *d) {
     const int r = d->radius;
     // >= 2r + 2 columns of replicated border: the symmetric kernel's virtual centres sit up to r columns outside the image and
@@ -154,7 +161,30 @@ static int alloc_records(smc_denoiser *d) {
     d->rec_pitch = ((d->W + 2 * d->padX + 15) / 16) * 16;
     d->rec_rows = d->H + 2 * r + 4;  // +4: rows only ever paired with out-of-range centre rows of the last tile
     d->rec_image_stride = (size_t)d->rec_rows * smc_rec_row_bytes(d->rec_pitch);
-    d->flags_offset = ((d->rec_image_stride * d->ptr_count + 255) / 256) * 256;
+    // Several scalar images over the same G-buffers (Estimator with ptrCount > 1: the ACRR radiance / albedo / ... statistics,
+    // one grid.z slice each in the reference, stat_denoiser.cu:422): three of them share one record -- image 3z + k in the slots
+    // of channel k of an RGB record -- and the symmetric kernel evaluates the G-buffer weight of a pair once for the three.
+    // Only where the symmetric kernel runs (Welch test, no RGB film, no acceptance counts, no external record halos);
+    // SMC_SYM_TRIPLE=0 keeps one record image per image.
+    d->tri = 0;
+    d->rec_images = d->ptr_count;
+    {
+        int pref = d->kernel_pref;
+        if (pref == 0 && getenv("SMC_FILTER_KERNEL")) pref = -1;
+        const char *e = getenv("SMC_SYM_TRIPLE");
+        if (d->C == 1 && d->ptr_count >= 2 && !d->denoise_film && !d->t_acc && !d->skip_top && !d->skip_bottom &&
+            (pref == 0 || pref == 3) && !(e && atoi(e) == 0)) {
+            SmcFilterParams p;
+            d->tri = 1;
+            d->rec_images = (d->ptr_count + 2) / 3;
+            fill_filter_params(d, p);
+            if (!smc_filter_sym_supported(p)) {
+                d->tri = 0;
+                d->rec_images = d->ptr_count;
+            }
+        }
+    }
+    d->flags_offset = ((d->rec_image_stride * d->rec_images + 255) / 256) * 256;
     const size_t bytes = d->flags_offset + 256;
     cudaError_t e = cudaMalloc(&d->d_rec, bytes);
     if (e != cudaSuccess)
@@ -175,7 +205,8 @@ static int alloc_records(smc_denoiser *d) {
 
 static void fill_filter_params(const smc_denoiser *d, SmcFilterParams &p) {
     p.W = d->W; p.H = d->H; p.C = d->C; p.NG = d->NG; p.radius = d->radius; p.mode = d->mode;
-    p.ptr_count = d->ptr_count; p.denoise_film = d->denoise_film; p.sm_count = d->ctx->sm_count;
+    p.ptr_count = d->rec_images; p.denoise_film = d->denoise_film; p.sm_count = d->ctx->sm_count;
+    p.tri = d->tri; p.images = d->ptr_count;
     p.row_begin = d->row_begin; p.row_end = d->row_end;
     p.padX = d->padX; p.rec_pitch = d->rec_pitch; p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec;
     p.sw = d->d_sw; p.sw_stride = d->sw_stride; p.sw_margin_y = SMC_SW_MARGIN_Y; p.sw_margin_x = SMC_SW_MARGIN_X;
@@ -203,6 +234,7 @@ static int select_kernel(smc_denoiser *d) {
         if (const char *e = getenv("SMC_FILTER_KERNEL")) pref = !strcmp(e, "stream") ? 2 : !strcmp(e, "generic") ? 1 : 0;
     d->use_sym = sym_ok && (pref == 0 || pref == 3);
     d->use_stream = !d->use_sym && ok && pref != 1;
+    if (d->tri && !d->use_sym) SMC_FAIL(SMC_ERR_UNSUPPORTED, "three-image records were laid out but the symmetric kernel is not selected");
     // output rows per thread: 2 x 2 pixels per thread wastes less work at the rim of the window (x1.06 at r = 20,
     // x1.23 at r = 6, against x1.13 / x1.46 for 2 x 4) and leaves room for 3 CTAs per SM; measured faster at every
     // radius tried (profiles/r1_variants.md).  SMC_STREAM_PY=4 selects the 2 x 4 variant for experiments.
@@ -371,6 +403,8 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     cudaFree(d->d_sym_sw);
     cudaFree(d->d_sym_rowrange);
     cudaFree(d->d_sym_scratch);
+    cudaFree(d->d_sym_scratch2);
+    cudaFree(d->d_sym_fwd2);
     cudaFree(d->d_sym_scratch_cnt);
     cudaFree(d->d_sym_fwd);
     cudaFree(d->d_sym_fwd_cnt);
@@ -392,7 +426,8 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo
     SmcPrepassParams p;
     std::memset(&p.halo, 0, sizeof(p.halo));
     p.halo_blocks = 0;
-    p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->ptr_count; p.radius = d->radius; p.mode = d->mode;
+    p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->rec_images; p.radius = d->radius; p.mode = d->mode;
+    p.triple = d->tri; p.images = d->ptr_count;
     p.denoise_film = d->denoise_film; p.padX = d->padX; p.rec_pitch = d->rec_pitch;
     p.rec_image_stride = d->rec_image_stride; p.rec = d->d_rec; p.skip_top = d->skip_top; p.skip_bottom = d->skip_bottom;
     p.pr_begin = y0 == 0 ? 0 : y0 + d->radius;
@@ -420,7 +455,7 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo
         const int r = d->radius, H = d->H;
         int rows = 0;
         for (int y = 0; y < H; y++) rows += ((up.rec && y < r) || (dn.rec && y >= H - r)) ? 1 : 0;
-        p.halo_blocks = rows * ((d->rec_pitch + 255) / 256) * d->ptr_count;
+        p.halo_blocks = rows * ((d->rec_pitch + 255) / 256) * d->rec_images;
     }
     return smc_launch_prepass(d->ctx, p);
 }
@@ -442,16 +477,20 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
         if (!smc_filter_sym_geometry(p, g, smem)) SMC_FAIL(SMC_ERR_UNSUPPORTED, "symmetric filter: geometry not supported");
         // scratch for the partial mirror sums and the forward sums of this row range (grown on demand; a launch over fewer
         // rows needs less)
-        const size_t se = smc_filter_sym_scratch_elems(p, g), fe = (size_t)d->ptr_count * (y1 - y0) * d->W;
+        const size_t se = smc_filter_sym_scratch_elems(p, g), fe = (size_t)d->rec_images * (y1 - y0) * d->W;
         if (se > d->sym_scratch_elems || fe > d->sym_fwd_elems) {
             SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));
             cudaFree(d->d_sym_scratch); cudaFree(d->d_sym_scratch_cnt); cudaFree(d->d_sym_fwd); cudaFree(d->d_sym_fwd_cnt);
+            cudaFree(d->d_sym_scratch2); cudaFree(d->d_sym_fwd2);
             d->d_sym_scratch = d->d_sym_fwd = nullptr;
+            d->d_sym_scratch2 = d->d_sym_fwd2 = nullptr;
             d->d_sym_scratch_cnt = d->d_sym_fwd_cnt = nullptr;
             d->sym_scratch_elems = d->sym_fwd_elems = 0;
             const size_t se2 = std::max(se, d->sym_scratch_elems), fe2 = std::max(fe, d->sym_fwd_elems);
             if (cudaMalloc(&d->d_sym_scratch, se2 * sizeof(float4)) != cudaSuccess ||
                 cudaMalloc(&d->d_sym_fwd, fe2 * sizeof(float4)) != cudaSuccess ||
+                (d->tri && (cudaMalloc(&d->d_sym_scratch2, se2 * sizeof(float2)) != cudaSuccess ||
+                            cudaMalloc(&d->d_sym_fwd2, fe2 * sizeof(float2)) != cudaSuccess)) ||
                 (d->t_acc && (cudaMalloc(&d->d_sym_scratch_cnt, se2 * sizeof(int)) != cudaSuccess ||
                               cudaMalloc(&d->d_sym_fwd_cnt, fe2 * sizeof(int)) != cudaSuccess))) {
                 cudaGetLastError();
@@ -463,6 +502,7 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
         }
         g.sw = d->d_sym_sw; g.rowrange = d->d_sym_rowrange; g.sw_special = d->sym_sw_special;
         g.scratch = d->d_sym_scratch; g.scratch_cnt = d->d_sym_scratch_cnt; g.fwd = d->d_sym_fwd; g.fwd_cnt = d->d_sym_fwd_cnt;
+        g.scratch2 = d->d_sym_scratch2; g.fwd2 = d->d_sym_fwd2;
         g.unit_counter = d->d_tile_counter;
         const char *nm = nullptr;
         const int rc = smc_launch_filter_sym(d->ctx, p, g, smem, &nm);
@@ -838,7 +878,7 @@ extern "C" int smc_denoiser_peer_attach_local(smc_denoiser *d, int which, smc_de
 
 extern "C" int smc_denoiser_halo(smc_denoiser *d, int z, int which, void **dev, size_t *bytes) {
     if (!d || !dev || !bytes) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
-    if (z < 0 || z >= d->ptr_count) SMC_FAIL(SMC_ERR_INVALID, "image %d out of range", z);
+    if (z < 0 || z >= d->rec_images) SMC_FAIL(SMC_ERR_INVALID, "record image %d out of range", z);
     const int r = d->radius;
     if (r > d->H) SMC_FAIL(SMC_ERR_UNSUPPORTED, "band of %d rows is shorter than the radius %d", d->H, r);
     const size_t row_bytes = smc_rec_row_bytes(d->rec_pitch);
@@ -862,7 +902,7 @@ extern "C" uint64_t smc_denoiser_pairs(const smc_denoiser *d) {
            (uint64_t)d->ptr_count;
 }
 
-extern "C" size_t smc_denoiser_record_bytes(const smc_denoiser *d) { return d ? d->rec_image_stride * d->ptr_count : 0; }
+extern "C" size_t smc_denoiser_record_bytes(const smc_denoiser *d) { return d ? d->rec_image_stride * d->rec_images : 0; }
 extern "C" const char *smc_denoiser_kernel_name(const smc_denoiser *d) { return d ? d->kernel_name : ""; }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -70,12 +70,14 @@ struct SymCentre {
     SmcCentre<C, NG> c;
     float2 v01, v2o;   // RGB statistics: (V.x, V.y), (V.z, 1);  scalar statistics: v01.x = the scalar value
     float2 n01, n2d;   // forward sums: (num.x, num.y), (num.z, den);  scalar statistics: n01.x = num, n2d.y = den
+    float2 d01;        // three scalar images per record (TRI): the denominators of images 0 and 1 (n2d = (num, den) of image 2)
     int cnt;
 };
 
 // mirror sums of one record, as they sit in the row buffer
 struct Mir {
     float2 m01, m2d;
+    float2 e;  // TRI: (num, den) of image 2; m01 = nums and m2d = dens of images 0 and 1
     int cnt;
 };
 
@@ -236,6 +238,59 @@ __device__ __forceinline__ void pair_mirror_only(const SymCentre<C, NG> &s, cons
     if (COUNT) m.cnt += ok ? 1 : 0;
 }
 
+// ---- three scalar images per record (TRI) ----------------------------------------------------------------------------------
+// The record has the RGB layout with image k in channel k's slots; the three membership tests gate three weights (instead of
+// one test over three channels gating one weight) and every image keeps its own denominator.
+template <int NG>
+__device__ __forceinline__ void sym_gate_tri(const SmcCentre<3, NG> &c, const SmcRec &r, float w, float &w0, float &w1, float &w2) {
+    const float2 sd = smc_add2(c.d01, make_float2(r.c0.z, r.c0.w));
+    const float2 pm = smc_mul2(c.t01, make_float2(r.c0.x, r.c0.y));
+    const float sz = __fadd_rn(c.dz, r.c1.y);
+    const float pz = __fmul_rn(c.tz, r.c1.x);
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.le.f32 p, %3, %4;\n"
+        "selp.f32 %0, %9, 0f00000000, p;\n"
+        "setp.le.f32 p, %5, %6;\n"
+        "selp.f32 %1, %9, 0f00000000, p;\n"
+        "setp.le.f32 p, %7, %8;\n"
+        "selp.f32 %2, %9, 0f00000000, p;\n"
+        "}\n"
+        : "=f"(w0), "=f"(w1), "=f"(w2)
+        : "f"(sd.x), "f"(pm.x), "f"(sd.y), "f"(pm.y), "f"(sz), "f"(pz), "f"(w));
+}
+
+template <int NG>
+__device__ __forceinline__ void pair_sym_tri(SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+    float w0, w1, w2;
+    sym_gate_tri<NG>(s.c, r, sym_weight<3, NG>(s.c, r, nsw), w0, w1, w2);
+    const float2 w01 = make_float2(w0, w1), w22 = make_float2(w2, w2);
+    s.n01 = smc_fma2(w01, make_float2(r.c2.x, r.c2.y), s.n01);
+    s.d01 = smc_add2(s.d01, w01);
+    m.m01 = smc_fma2(w01, s.v01, m.m01);
+    m.m2d = smc_add2(m.m2d, w01);
+    if (NG <= 6) {
+        s.n2d = smc_fma2(w22, make_float2(r.c1.z, r.c1.w), s.n2d);  // record slot 7 == 1.0f
+        m.e = smc_fma2(w22, s.v2o, m.e);
+    } else {
+        s.n2d.x = __fmaf_rn(w2, r.c1.z, s.n2d.x);
+        s.n2d.y = __fadd_rn(s.n2d.y, w2);
+        m.e.x = __fmaf_rn(w2, s.v2o.x, m.e.x);
+        m.e.y = __fadd_rn(m.e.y, w2);
+    }
+}
+
+template <int NG>
+__device__ __forceinline__ void pair_mirror_only_tri(const SymCentre<3, NG> &s, const SmcRec &r, float2 nsw, Mir &m) {
+    float w0, w1, w2;
+    sym_gate_tri<NG>(s.c, r, sym_weight<3, NG>(s.c, r, nsw), w0, w1, w2);
+    const float2 w01 = make_float2(w0, w1);
+    m.m01 = smc_fma2(w01, s.v01, m.m01);
+    m.m2d = smc_add2(m.m2d, w01);
+    m.e.x = __fmaf_rn(w2, s.v2o.x, m.e.x);
+    m.e.y = __fadd_rn(m.e.y, w2);
+}
+
 struct SymTile {
     int z, sx, uy, k, nt;       // image, strip, unit row, tile within the unit, tiles of the unit
     int x0, y0, i0, nrt;        // first centre column / row, first streamed row index, streamed rows
@@ -307,7 +362,7 @@ __device__ __forceinline__ void zpair_eval(const ZPair &z, const SmcRec &r, floa
 }
 
 // One record row (already in the warp's ring slot; the mirror buffer holds zeros) against the warp's 2 x 2 centres per lane.
-template <int C, int NG, bool COUNT>
+template <int C, int NG, bool COUNT, bool TRI>
 __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymParams &g, SymCentre<C, NG> (&cen)[2][2],
                                         const ZPair (&zp)[2], const int2 *rowrange, const float2 *sw, const unsigned char *slot, float4 *macc,
                                         int *mcnt, int i, int base_idx) {
@@ -328,19 +383,27 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
         float4 *mp0 = macc + par * half + (first >> 1);               // sums of record `first`, then first + 2, ...
         float4 *mp1 = macc + (par ^ 1) * half + ((first + 1) >> 1);   // sums of record first + 1, first + 3, ...
         int *cp0 = mcnt + par * half + (first >> 1), *cp1 = mcnt + (par ^ 1) * half + ((first + 1) >> 1);
+        // TRI: the third image's (num, den) sit in a float2 array of the same indexing that takes the count array's place
+        float2 *ep0 = (float2 *)mcnt + par * half + (first >> 1), *ep1 = (float2 *)mcnt + (par ^ 1) * half + ((first + 1) >> 1);
         SmcRec cur = lds_rec(rp);
         // (centre kx = 0 sees the record at dx = j, centre kx = 1 at dx = j - 1: the table value of the previous step)
-        auto load_m = [&](const float4 *mp, const int *cp) {
+        auto load_m = [&](const float4 *mp, const int *cp, const float2 *ep) {
             const float4 mv = *mp;
             Mir m;
             m.m01 = make_float2(mv.x, mv.y);
             m.m2d = make_float2(mv.z, mv.w);
+            m.e = TRI ? *ep : make_float2(0.f, 0.f);
             m.cnt = COUNT ? *cp : 0;
             return m;
         };
-        auto store_m = [&](float4 *mp, int *cp, const Mir &m) {
+        auto store_m = [&](float4 *mp, int *cp, float2 *ep, const Mir &m) {
             *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
+            if (TRI) *ep = m.e;
             if (COUNT) *cp = m.cnt;
+        };
+        auto pair = [&](SymCentre<C, NG> &sc, const SmcRec &rec, float2 nsw, Mir &m, float sz, float pz) {
+            if constexpr (TRI) pair_sym_tri<NG>(sc, rec, nsw, m);
+            else pair_sym<C, NG, COUNT>(sc, rec, nsw, m, sz, pz);
         };
         int j = lo;
         for (; j + 1 <= hi; j += 2) {
@@ -349,41 +412,41 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
             const SmcRec nxt = lds_rec(rp + d0);
             const float2 a0 = swp0[0], a1 = swp1[0], b0 = swp0[1], b1 = swp1[1];
             sym_order();
-            Mir ma = load_m(mp0, cp0), mb = load_m(mp1, cp1);
+            Mir ma = load_m(mp0, cp0, ep0), mb = load_m(mp1, cp1, ep1);
             float2 sa0, pa0, sa1, pa1, sb0, pb0, sb1, pb1;  // z-channel test operands: (column 0, column 1) per record and row
             zpair_eval<C>(zp[0], cur, sa0, pa0);
             zpair_eval<C>(zp[1], cur, sa1, pa1);
             zpair_eval<C>(zp[0], nxt, sb0, pb0);
             zpair_eval<C>(zp[1], nxt, sb1, pb1);
-            pair_sym<C, NG, COUNT>(cen[0][0], cur, a0, ma, sa0.x, pa0.x);
-            pair_sym<C, NG, COUNT>(cen[0][0], nxt, b0, mb, sb0.x, pb0.x);
-            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
-            pair_sym<C, NG, COUNT>(cen[0][1], nxt, a0, mb, sb0.y, pb0.y);
-            pair_sym<C, NG, COUNT>(cen[1][0], cur, a1, ma, sa1.x, pa1.x);
-            pair_sym<C, NG, COUNT>(cen[1][0], nxt, b1, mb, sb1.x, pb1.x);
-            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
-            pair_sym<C, NG, COUNT>(cen[1][1], nxt, a1, mb, sb1.y, pb1.y);
-            store_m(mp0, cp0, ma);
-            store_m(mp1, cp1, mb);
+            pair(cen[0][0], cur, a0, ma, sa0.x, pa0.x);
+            pair(cen[0][0], nxt, b0, mb, sb0.x, pb0.x);
+            pair(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
+            pair(cen[0][1], nxt, a0, mb, sb0.y, pb0.y);
+            pair(cen[1][0], cur, a1, ma, sa1.x, pa1.x);
+            pair(cen[1][0], nxt, b1, mb, sb1.x, pb1.x);
+            pair(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
+            pair(cen[1][1], nxt, a1, mb, sb1.y, pb1.y);
+            store_m(mp0, cp0, ep0, ma);
+            store_m(mp1, cp1, ep1, mb);
             sym_order();
             rp += SMC_LINE_BYTES;
             cur = lds_rec(rp);  // record j + 2 (one past the end stays inside the slot)
             sw_prev0 = b0;
             sw_prev1 = b1;
             swp0 += 2; swp1 += 2;
-            mp0++; mp1++; cp0++; cp1++;
+            mp0++; mp1++; cp0++; cp1++; ep0++; ep1++;
         }
         if (j <= hi) {
             sym_order();
-            Mir ma = load_m(mp0, cp0);
+            Mir ma = load_m(mp0, cp0, ep0);
             float2 sa0, pa0, sa1, pa1;
             zpair_eval<C>(zp[0], cur, sa0, pa0);
             zpair_eval<C>(zp[1], cur, sa1, pa1);
-            pair_sym<C, NG, COUNT>(cen[0][0], cur, swp0[0], ma, sa0.x, pa0.x);
-            pair_sym<C, NG, COUNT>(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
-            pair_sym<C, NG, COUNT>(cen[1][0], cur, swp1[0], ma, sa1.x, pa1.x);
-            pair_sym<C, NG, COUNT>(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
-            store_m(mp0, cp0, ma);
+            pair(cen[0][0], cur, swp0[0], ma, sa0.x, pa0.x);
+            pair(cen[0][1], cur, sw_prev0, ma, sa0.y, pa0.y);
+            pair(cen[1][0], cur, swp1[0], ma, sa1.x, pa1.x);
+            pair(cen[1][1], cur, sw_prev1, ma, sa1.y, pa1.y);
+            store_m(mp0, cp0, ep0, ma);
             sym_order();
         }
     }
@@ -396,14 +459,18 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
             const SmcRec rec = lds_rec(slot + smc_rec_offset(idx));
             float4 *mp = macc + (idx & 1) * half + (idx >> 1);
             int *cp = mcnt + (idx & 1) * half + (idx >> 1);
+            float2 *ep = (float2 *)mcnt + (idx & 1) * half + (idx >> 1);
             __syncwarp();
             const float4 mv = *mp;
             Mir m;
             m.m01 = make_float2(mv.x, mv.y);
             m.m2d = make_float2(mv.z, mv.w);
+            m.e = TRI ? *ep : make_float2(0.f, 0.f);
             m.cnt = COUNT ? *cp : 0;
-            pair_mirror_only<C, NG, COUNT>(kx ? s1 : s0, rec, nsw, m);
+            if constexpr (TRI) pair_mirror_only_tri<NG>(kx ? s1 : s0, rec, nsw, m);
+            else pair_mirror_only<C, NG, COUNT>(kx ? s1 : s0, rec, nsw, m);
             *mp = make_float4(m.m01.x, m.m01.y, m.m2d.x, m.m2d.y);
+            if (TRI) *ep = m.e;
             if (COUNT) *cp = m.cnt;
         }
     };
@@ -413,7 +480,7 @@ __device__ __forceinline__ void sym_row(const SmcFilterParams &p, const SmcSymPa
     if (i == r + 1) special(cen[1][0], cen[1][1], 0);
 }
 
-template <int C, int NG, bool COUNT>
+template <int C, int NG, bool COUNT, bool TRI>
 __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFilterParams p, const SmcSymParams g) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [per warp: 2 record slots | 2 x 2 spatial-table rows | mirror buffer (| count buffer)] ... [rowrange]
@@ -489,6 +556,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
     for (int e = lane; e < g.seg_rec; e += 32) {
         macc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (COUNT) mcnt[e] = 0;
+        if (TRI) ((float2 *)mcnt)[e] = make_float2(0.f, 0.f);
     }
 
     uint32_t pos = 0;  // rows consumed so far: ring slot = pos & 1, phase parity = (pos >> 1) & 1
@@ -521,6 +589,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                 // the centre tap: weight 1 unconditionally (is_center, stat_denoiser.cu:78, :318-323)
                 s.n01 = real ? s.v01 : make_float2(0.f, 0.f);
                 s.n2d = real ? s.v2o : make_float2(0.f, 0.f);
+                s.d01 = (TRI && real) ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
                 s.cnt = real ? 1 : 0;
             }
 
@@ -551,7 +620,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                     : "memory");
             }
             __syncwarp();  // lanes leave the wait loop one by one: run the row converged (see sym_order())
-            sym_row<C, NG, COUNT>(p, g, cen, zp, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
+            sym_row<C, NG, COUNT, TRI>(p, g, cen, zp, rowrange, (const float2 *)(swb0 + (size_t)s * sw_bytes), ring + (size_t)s * g.slot_bytes,
                                   macc, mcnt, i, base_idx);
             __syncwarp();  // every lane has read the slot and written its mirror sums
             // Flush the row's mirror sums into the unit's scratch: plain loads and stores by the lanes.  Entry e is always
@@ -559,17 +628,21 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
             // stored itself one tile earlier: program order is all the ordering this needs.  The loads of up to four entries
             // per lane are issued together, and lane 0 queues the next TMA copies while they are in flight.
             int *scc = COUNT ? g.scratch_cnt + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec : nullptr;
+            float2 *sce = TRI ? g.scratch2 + ti.scr0 + (size_t)(ti.y0 + i - ti.yfirst) * g.seg_rec : nullptr;
             for (int e0 = 0; e0 < g.seg_rec; e0 += 128) {
                 float4 o[4];
+                float2 oe[4];
                 int oc[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int e = e0 + 32 * k + lane;
                     o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    oe[k] = make_float2(0.f, 0.f);
                     oc[k] = 0;
                     if (!first && e < g.seg_rec) {
                         o[k] = __ldcg(sc + e);
                         if (COUNT) oc[k] = __ldcg(scc + e);
+                        if (TRI) oe[k] = __ldcg(sce + e);
                     }
                 }
                 if (e0 == 0 && lane == 0) {  // queue stream position pos + 2 into the slot every lane has just left
@@ -600,6 +673,11 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                             mcnt[e] = 0;
                             __stcg(scc + e, c + oc[k]);
                         }
+                        if (TRI) {
+                            const float2 ve = ((float2 *)mcnt)[e];
+                            ((float2 *)mcnt)[e] = make_float2(0.f, 0.f);
+                            __stcg(sce + e, first ? ve : make_float2(__fadd_rn(oe[k].x, ve.x), __fadd_rn(oe[k].y, ve.y)));
+                        }
                     }
                 }
             }
@@ -615,7 +693,12 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
                 if (yc >= p.row_begin && yc < p.row_end && xc >= 0 && xc < p.W) {
                     const SymCentre<C, NG> &s = cen[ky][kx];
                     const size_t o = ((size_t)ti.z * rows_out + (yc - p.row_begin)) * p.W + xc;
-                    g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.n2d.x, s.n2d.y);
+                    if (TRI) {
+                        g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.d01.x, s.d01.y);
+                        g.fwd2[o] = s.n2d;
+                    } else {
+                        g.fwd[o] = make_float4(s.n01.x, s.n01.y, s.n2d.x, s.n2d.y);
+                    }
                     if (COUNT) g.fwd_cnt[o] = s.cnt;
                 }
             }
@@ -631,7 +714,7 @@ __global__ void __launch_bounds__(kSymThreads, 1) filter_sym_kernel(const SmcFil
 }
 
 // out(y, x) = (forward sums + every partial mirror sum that covers the pixel) / den   (stat_denoiser.cu:341-344)
-template <int C, bool COUNT>
+template <int C, bool COUNT, bool TRI>
 __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p, const SmcSymParams g) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = p.row_begin + blockIdx.y;
@@ -640,6 +723,7 @@ __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p
     const int r = p.radius, rows_out = p.row_end - p.row_begin;
     const size_t o = ((size_t)z * rows_out + (y - p.row_begin)) * p.W + x;
     float4 s = g.fwd[o];
+    float2 se = TRI ? g.fwd2[o] : make_float2(0.f, 0.f);
     int cnt = COUNT ? g.fwd_cnt[o] : 0;
     // tiles whose centre rows y - r .. y stream row y; strips whose centres reach column x
     const int tlo = (y - r - g.ystart) >> 1, thi = min(g.n_trows - 1, (y - g.ystart) >> 1);
@@ -658,7 +742,22 @@ __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p
             s.z = __fadd_rn(s.z, v.z);
             s.w = __fadd_rn(s.w, v.w);
             if (COUNT) cnt += __ldg(g.scratch_cnt + q);
+            if (TRI) {
+                const float2 ve = __ldg(g.scratch2 + q);
+                se.x = __fadd_rn(se.x, ve.x);
+                se.y = __fadd_rn(se.y, ve.y);
+            }
         }
+    }
+    if (TRI) {  // three scalar images: s = (num0, num1, den0, den1), se = (num2, den2)
+        const float num[3] = {s.x, s.y, se.x}, den[3] = {s.z, s.w, se.y};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (3 * z + k < g.images) {
+                const SmcPtrStepSz ob = p.out_ptrs[3 * z + k];
+                ((float *)(ob.data + (size_t)y * ob.step))[x] = __fdiv_rn(num[k], den[k]);
+            }
+        return;
     }
     if (C == 3) {
         const SmcPtrStepSz ob = (p.denoise_film && z == 0) ? p.film_filtered : p.out_ptrs[z];
@@ -675,12 +774,16 @@ __global__ void __launch_bounds__(128) sym_gather_kernel(const SmcFilterParams p
 
 template <int C, int NG>
 int launch_sym_ng(smc_context *ctx, const SmcFilterParams &p, const SmcSymParams &g, size_t smem, int grid) {
-    if (p.accepted != nullptr) {
-        auto k = filter_sym_kernel<C, NG, true>;
+    if (C == 3 && g.tri) {
+        auto k = filter_sym_kernel<3, NG, false, true>;
+        SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
+    } else if (p.accepted != nullptr) {
+        auto k = filter_sym_kernel<C, NG, true, false>;
         SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
     } else {
-        auto k = filter_sym_kernel<C, NG, false>;
+        auto k = filter_sym_kernel<C, NG, false, false>;
         SMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, g.nwarps * 32, smem, ctx->stream>>>(p, g);
     }
@@ -709,6 +812,7 @@ bool smc_filter_sym_supported(const SmcFilterParams &p) {
     if (p.mode != SMC_MEMBER_WELCH) return false;  // the Moon test is not symmetric (stat_denoiser.cu:132-143)
     // scalar statistics: unless image 0 also filters the RGB film (five sums per tap: the one-sided per-warp kernel does that)
     if (!(p.C == 3 || (p.C == 1 && !p.denoise_film))) return false;
+    if (p.tri && (p.C != 1 || p.accepted != nullptr)) return false;
     if (p.radius < 2 || p.radius > SMC_MAX_RADIUS) return false;
     if (p.NG < 0 || p.NG > 7 || p.NGX > 0) return false;
     if ((p.padX & 1) || (p.rec_pitch & 1)) return false;
@@ -722,6 +826,8 @@ bool smc_filter_sym_supported(const SmcFilterParams &p) {
 // fills everything of `g` that follows from the filter parameters (tables, scratch pointers and counters are the caller's)
 bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &smem) {
     const int r = p.radius;
+    g.tri = p.tri;
+    g.images = p.images;
     g.xorg = -(r + (r & 1));
     g.n_strips = (p.W + r - g.xorg + kTW - 1) / kTW;
     g.ystart = p.row_begin - r;
@@ -734,7 +840,7 @@ bool smc_filter_sym_geometry(const SmcFilterParams &p, SmcSymParams &g, size_t &
     g.sw_mx = 2;
     g.sw_rows = r + 1 + 2 * g.sw_my;
     g.sw_stride = 2 * r + 2 + 2 * g.sw_mx;  // even: two table rows of 8-byte entries move as one 16-byte-aligned bulk copy
-    g.warp_bytes = 2 * g.slot_bytes + 2 * (2 * g.sw_stride * 8) + g.macc_bytes + (count ? g.seg_rec * 4 : 0);
+    g.warp_bytes = 2 * g.slot_bytes + 2 * (2 * g.sw_stride * 8) + g.macc_bytes + (g.tri ? g.seg_rec * 8 : count ? g.seg_rec * 4 : 0);
     g.warp_bytes = ((g.warp_bytes + 127) / 128) * 128;
     const size_t tables = (size_t)g.sw_rows * 8;
     const size_t avail = 227 * 1024 - 1024;
@@ -782,19 +888,22 @@ int smc_launch_filter_sym(smc_context *ctx, const SmcFilterParams &p, const SmcS
     const int rows = p.row_end - p.row_begin;
     if (rows <= 0) return SMC_OK;
     static thread_local char nm[80];
-    snprintf(nm, sizeof(nm), "sym-warp<%sNG=%d,PY=2,welch,W=%d,U=%d/%d>", p.C == 1 ? "C=1," : "", p.NG, g.nwarps, g.u_big, g.u_small);
+    snprintf(nm, sizeof(nm), "sym-warp<%sNG=%d,PY=2,welch,W=%d,U=%d/%d>", g.tri ? "C=1x3," : p.C == 1 ? "C=1," : "", p.NG, g.nwarps,
+             g.u_big, g.u_small);
     if (name) *name = nm;
     const int grid = (int)std::min<long long>((g.units_total + g.nwarps - 1) / g.nwarps, (long long)ctx->sm_count);
     SMC_CUDA(cudaMemsetAsync(g.unit_counter, 0, sizeof(int), ctx->stream));
-    const int rc = p.C == 3 ? launch_sym_c<3>(ctx, p, g, smem, grid) : launch_sym_c<1>(ctx, p, g, smem, grid);
+    const int rc = (p.C == 3 || g.tri) ? launch_sym_c<3>(ctx, p, g, smem, grid) : launch_sym_c<1>(ctx, p, g, smem, grid);
     if (rc) return rc;
     const dim3 gb(128), gg((p.W + 127) / 128, rows, p.ptr_count);
-    if (p.C == 3) {
-        if (p.accepted != nullptr) sym_gather_kernel<3, true><<<gg, gb, 0, ctx->stream>>>(p, g);
-        else sym_gather_kernel<3, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+    if (g.tri) {
+        sym_gather_kernel<3, false, true><<<gg, gb, 0, ctx->stream>>>(p, g);
+    } else if (p.C == 3) {
+        if (p.accepted != nullptr) sym_gather_kernel<3, true, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+        else sym_gather_kernel<3, false, false><<<gg, gb, 0, ctx->stream>>>(p, g);
     } else {
-        if (p.accepted != nullptr) sym_gather_kernel<1, true><<<gg, gb, 0, ctx->stream>>>(p, g);
-        else sym_gather_kernel<1, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+        if (p.accepted != nullptr) sym_gather_kernel<1, true, false><<<gg, gb, 0, ctx->stream>>>(p, g);
+        else sym_gather_kernel<1, false, false><<<gg, gb, 0, ctx->stream>>>(p, g);
     }
     SMC_CHECK_LAUNCH(ctx);
     return SMC_OK;

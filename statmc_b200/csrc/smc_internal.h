@@ -145,6 +145,9 @@ struct SmcFilterParams {
     int ptr_count;
     int denoise_film;
     int sm_count;          // SMs of the device (work partitioning heuristics)
+    // three scalar images per record (symmetric kernel only): ptr_count counts record images = triples, `images` the plan's
+    // images (out_ptrs has `images` entries, image 3z + k sits in channel k's slots of record image z)
+    int tri, images;
     int row_begin, row_end;
     int padX;              // record columns left of x = 0
     int rec_pitch;         // records per record row
@@ -184,11 +187,16 @@ struct SmcSymParams {
     int *scratch_cnt;  // same indexing: partial accepted-tap counts (only with an `accepted` plane)
     float4 *fwd;       // [image][row_end - row_begin][W]: forward sums
     int *fwd_cnt;
+    // three scalar images per record (copied from SmcFilterParams by smc_filter_sym_geometry): the scratch / forward entries
+    // are (num0, num1, den0, den1) and the third image's (num2, den2) goes to scratch2 / fwd2
+    int tri, images;
+    float2 *scratch2, *fwd2;
     int *unit_counter;
 };
 
 struct SmcPrepassParams {
     int W, H, C, ptr_count, radius, mode, denoise_film;
+    int triple, images;  // scalar statistics, three images per record: ptr_count counts triples, `images` the images
     int padX, rec_pitch;
     size_t rec_image_stride;
     unsigned char *rec;

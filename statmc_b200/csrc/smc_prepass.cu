@@ -38,6 +38,11 @@ __device__ __forceinline__ float lut_t(const float *__restrict__ lut, int idx) {
 // smc_fastdiv.cuh).
 template <int C, int NG>
 __device__ __forceinline__ void prepass_pixel(const SmcPrepassParams &p, const int pc, const int pr, const int z);
+template <int NG>
+__device__ __forceinline__ void prepass_pixel_triple(const SmcPrepassParams &p, const int pc, const int pr, const int z);
+template <int NG>
+__device__ __forceinline__ void prepass_finish(const SmcPrepassParams &p, float (&rec)[SMC_REC_FLOATS], const float (&g)[NG > 0 ? NG : 1],
+                                               const int pc, const int pr, const int z, const int yy, const int y, const int x);
 
 template <int C, int NG>
 __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
@@ -60,7 +65,10 @@ __global__ void __launch_bounds__(256) prepass_kernel(SmcPrepassParams p) {
     }
     const bool idle = pc >= p.rec_pitch || (yy < 0 && p.skip_top) || (yy >= p.H && p.skip_bottom);
     if (idle && !(to_up || to_dn)) return;
-    if (!idle) prepass_pixel<C, NG>(p, pc, pr, z);
+    if (!idle) {
+        if (C == 1 && p.triple) prepass_pixel_triple<NG>(p, pc, pr, z);
+        else prepass_pixel<C, NG>(p, pc, pr, z);
+    }
     if (to_up || to_dn) {  // block-uniform
         __threadfence_system();  // this thread's peer stores before the block's signal
         __syncthreads();
@@ -166,6 +174,53 @@ __device__ __forceinline__ void prepass_pixel(const SmcPrepassParams &p, const i
         rec[4] = val[0];
         rec[8] = film[0]; rec[9] = film[1]; rec[6] = film[2];
     }
+    prepass_finish<NG>(p, rec, g, pc, pr, z, yy, y, x);
+}
+
+// Scalar statistics, three images per record (SmcPrepassParams::triple): image 3z + k goes where channel k of an RGB image
+// would -- Johnson-corrected mean in slots 0 / 1 / 4, discriminator in 2 / 3 / 5, value in 8 / 9 / 6 -- so that the filter
+// evaluates the G-buffer weight of a pair once for the three of them (the weight does not depend on the image, only the
+// membership does; the reference launches one grid.z slice per image over the same G-buffers, stat_denoiser.cu:422).
+template <int NG>
+__device__ __forceinline__ void prepass_pixel_triple(const SmcPrepassParams &p, const int pc, const int pr, const int z) {
+    const int yy = pr - p.radius;
+    const int y = min(max(yy, 0), p.H - 1);
+    const int x = min(max(pc - p.padX, 0), p.W - 1);
+    const bool own = (yy == y) && (pc - p.padX == x);
+    float g[NG > 0 ? NG : 1];
+#pragma unroll
+    for (int k = 0; k < NG; k++) g[k] = rowf(p.gbufs[p.g_buf[k]], y)[x * p.g_nch[k] + p.g_ch[k]];
+    float rec[SMC_REC_FLOATS];
+#pragma unroll
+    for (int i = 0; i < SMC_REC_FLOATS; i++) rec[i] = 0.f;
+    constexpr int ms[3] = {0, 1, 4}, ds[3] = {2, 3, 5}, vs[3] = {8, 9, 6};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int img = min(3 * z + k, p.images - 1);  // a triple beyond the last image repeats it; its results are dropped
+        const int n = rowi(p.n[img], y)[x];
+        const float mean = rowf(p.mean[img], y)[x], m2 = rowf(p.m2[img], y)[x], m3 = rowf(p.m3[img], y)[x];
+        const float val = rowf(p.film_ptrs[img], y)[x];
+        const float t = lut_t(p.lut, 2 * n - 3);
+        const float nF = __int2float_rn(n), nm1 = __fsub_rn(nF, 1.f), nn1 = __fmul_rn(nF, nm1);
+        const float s2 = __fdiv_rn(m2, nm1);  // stat_denoiser.cu:179
+        float corr = 0.f;
+        if (s2 > FLT_EPSILON) corr = __fdiv_rn(__fdiv_rn(m3, nF), __fmul_rn(__fmul_rn(6.f, s2), nF));  // :114-116
+        const float m = __fadd_rn(mean, corr);                                                              // :181
+        const float d = __fsub_rn(__fmul_rn(m, m), __fdiv_rn(__fmul_rn(__fmul_rn(t, t), m2), nn1));        // :205
+        if (own && 3 * z + k < p.images) {
+            if (p.mean_corr && p.mean_corr[img].data) rowf_w(p.mean_corr[img], y)[x] = m;
+            if (p.disc && p.disc[img].data) rowf_w(p.disc[img], y)[x] = d;
+        }
+        rec[ms[k]] = m;
+        rec[ds[k]] = d;
+        rec[vs[k]] = val;
+    }
+    prepass_finish<NG>(p, rec, g, pc, pr, z, yy, y, x);
+}
+
+template <int NG>
+__device__ __forceinline__ void prepass_finish(const SmcPrepassParams &p, float (&rec)[SMC_REC_FLOATS], const float (&g)[NG > 0 ? NG : 1],
+                                               const int pc, const int pr, const int z, const int yy, const int y, const int x) {
     // G-buffers, flattened and pre-scaled so that  sum_k (g'_C - g'_I)^2 = -log2(e) * sum_g drFactor_g |g_C - g_I|^2
     // (dr2, stat_denoiser.cu:90-112); the filter then needs one subtraction and one FMA per channel and no factor.
     // g_scale[k] = sqrtf(-drFactor * log2(e)) is computed once on the host.

@@ -256,6 +256,45 @@ def test_scalar_stream_matches_generic(ctx, W, H, r, names, membership):
         assert rel_mad(res[2][0], ref) <= TOL
 
 
+@pytest.mark.parametrize("pc,W,H,r,names", [(2, 150, 37, 6, ("normal", "albedo")), (3, 333, 47, 20, ("normal", "albedo")),
+                                            (5, 130, 40, 9, ("normal", "albedo", "depth")), (7, 64, 33, 3, ())])
+def test_scalar_image_triples(ctx, monkeypatch, pc, W, H, r, names):
+    """ptrCount > 1 scalar images over shared G-buffers (the ACRR statistics; one grid.z slice each in the reference,
+    stat_denoiser.cu:422): the symmetric kernel packs three images per record and evaluates a pair's G-buffer weight once for
+    the three.  Against one record image per image (SMC_SYM_TRIPLE=0), and each image against the oracle."""
+    src = [synth.moment_buffers(W, H, n=12 + 9 * k, config_id=70 + k, vary_n=(k % 2 == 1)) for k in range(pc)]
+    ch = lambda k, a: np.ascontiguousarray(a[..., k % 3])
+    up = lambda a: Buffer.from_array(ctx, a)
+    dev = [{q: up(ch(k, s[q])) for q in ("mean", "m2", "m3")} for k, s in enumerate(src)]
+    ns, vals = [up(s["n"]) for s in src], [up(ch(k, s["film"])) for k, s in enumerate(src)]
+    gsrc = src[0]
+    g = [up(gsrc[k]) for k in names]
+    f = [po.f32_factor({"normal": 0.1, "albedo": 0.02, "depth": 0.5}[k]) for k in names]
+    res = {}
+    for triple in ("1", "0"):
+        monkeypatch.setenv("SMC_SYM_TRIPLE", triple)
+        outs, mcs, dcs = ([Buffer(ctx, H, W, 1) for _ in range(pc)] for _ in range(3))
+        dn = Denoiser(ctx, channels=1, width=W, height=H, radius=r, ds_factor=po.f32_factor(r / 2.0), n=ns,
+                      mean=[d["mean"] for d in dev], m2=[d["m2"] for d in dev], m3=[d["m3"] for d in dev], film_ptrs=vals,
+                      gbufs=g, gbuf_dr_factors=f, film_filtered_ptrs=outs, mean_corr=mcs, disc=dcs, denoise_film=False, kernel=0)
+        dn.run()
+        dn.run()  # a plan is reusable: scratch and counters are reset per launch
+        ctx.synchronize()
+        assert ("sym-warp<C=1x3" in dn.kernel_name) == (triple == "1"), dn.kernel_name
+        res[triple] = [[b.download() for b in lst] for lst in (outs, mcs, dcs)]
+        dn.close()
+    for k in range(pc):
+        # same arithmetic; the mirror sums are grouped by other work units, hence summed in another order
+        assert _same_rows(res["1"][0][k], res["0"][0][k], 3)
+        assert bits_equal(res["1"][1][k], res["0"][1][k]) and bits_equal(res["1"][2][k], res["0"][2][k])
+    for k, s in enumerate(src):
+        mc, dc = po.prepass(s["n"], ch(k, s["mean"]), ch(k, s["m2"]), ch(k, s["m3"]))
+        ref = po.filter(ch(k, s["film"]), [gsrc[q] for q in names], f, r, po.f32_factor(r / 2.0), mean_corr=mc, disc=dc,
+                        precision="f64")
+        ok = s["n"] >= 2
+        assert rel_mad(res["1"][0][k][ok], ref[ok]) <= TOL, k
+
+
 def test_multi_image_rgb_routing(ctx):
     # filter<float3>, ptrCount = 2, denoiseFilm: image 0 filters `film` into film-f and leaves filmFilteredPtrs[0]
     # untouched (stat_denoiser.cu:319-344); image 1 filters filmPtrs[1] into filmFilteredPtrs[1].

@@ -70,8 +70,8 @@ def test_symmetric_kernel_inner_loop():
     whose body holds eight MUFU.EX2) the 16-byte loads of the two row-buffer entries precede the eight pair evaluations and
     their 16-byte stores follow them, with no row-buffer load hoisted across the loop's stores (smc_filter_sym.cu: sym_order())."""
     f = _functions(_run("-sass"))
-    sym = [k for k in f if "filter_sym_kernelILi3ELi6ELb0E" in k]
-    assert len(sym) == 1, "default RGB symmetric instantiation <C=3,NG=6,no count>"
+    sym = [k for k in f if "filter_sym_kernelILi3ELi6ELb0ELb0E" in k]
+    assert len(sym) == 1, "default RGB symmetric instantiation <C=3,NG=6,no count,one image per record>"
     lines = f[sym[0]]
     text = "\n".join(lines)
     assert "UBLKCP" in text and "SYNCS" in text and "MUFU.EX2" in text
