@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "statmc_b200", "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(ROOT, "statmc_b200", "libstatmc_b200.so")
-SOURCES = ["smc_context.cu", "smc_moments.cu", "smc_prepass.cu", "smc_filter_generic.cu", "smc_filter_stream.cu", "smc_filter_sym.cu",
+SOURCES = ["smc_context.cu", "smc_moments.cu", "smc_prepass.cu", "smc_filter_generic.cu", "smc_filter_fixup.cu", "smc_filter_stream.cu", "smc_filter_sym.cu",
            "smc_denoiser.cu", "smc_tcdf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]

@@ -185,7 +185,8 @@ static int alloc_records(smc_denoiser *d) {
         }
     }
     d->flags_offset = ((d->rec_image_stride * d->rec_images + 255) / 256) * 256;
-    const size_t bytes = d->flags_offset + 256;
+    // [records | halo flags | two lists of non-finite values (SmcNfList, step parity)]
+    const size_t bytes = d->flags_offset + SMC_NF_OFFSET + 2 * sizeof(SmcNfList);
     cudaError_t e = cudaMalloc(&d->d_rec, bytes);
     if (e != cudaSuccess)
         SMC_FAIL(SMC_ERR_NOMEM, "cudaMalloc(%zu bytes of records) failed: %s", bytes, cudaGetErrorString(e));
@@ -420,10 +421,16 @@ extern "C" void smc_denoiser_destroy(smc_denoiser *d) {
     delete d;
 }
 
+static bool has_peers(const smc_denoiser *d);
+static SmcNfList *nf_list(const smc_denoiser *d, const int *flags);
+
 // prepass over image rows [y0, y1); the replicated rows above row 0 / below row H-1 go with the first / last rows
 static int prepass_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo = nullptr) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
     SmcPrepassParams p;
+    p.nf = nf_list(d, d->d_flags);
+    // a frame's first rows start its list of non-finite values (row chunks of one frame come in ascending order)
+    if (y0 == 0) SMC_CUDA(cudaMemsetAsync(&p.nf->count, 0, sizeof(int), d->ctx->stream));
     std::memset(&p.halo, 0, sizeof(p.halo));
     p.halo_blocks = 0;
     p.W = d->W; p.H = d->H; p.C = d->C; p.ptr_count = d->rec_images; p.radius = d->radius; p.mode = d->mode;
@@ -462,13 +469,46 @@ static int prepass_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo
 
 static bool has_peers(const smc_denoiser *d) { return d->peer[0].rec || d->peer[1].rec; }
 
+// the list of non-finite values of the current frame: with peer halos the two lists alternate with the protocol's step, so
+// that a neighbour can still read the entries of its halo rows while this rank lists the next frame
+static SmcNfList *nf_list(const smc_denoiser *d, const int *flags) {
+    return (SmcNfList *)((unsigned char *)flags + SMC_NF_OFFSET) + (has_peers(d) ? (d->step & 1) : 0);
+}
+
+// the listed non-finite values of this frame go to the centres of rows [p.row_begin, p.row_end) they are member taps of
+static int nonfinite_fixup(const smc_denoiser *d, SmcFilterParams p, const SmcHaloSync &release) {
+    // with peer halos this kernel, not the filter, releases the neighbours' halo rows: it still reads records of the halo
+    p.halo = release;
+    SmcNfSources src;
+    std::memset(&src, 0, sizeof(src));
+    const int r = d->radius;
+    src.list[0] = nf_list(d, d->d_flags);
+    src.row_lo[0] = 0; src.row_hi[0] = 1 << 30; src.row_shift[0] = 0;
+    if (d->peer[0].rec) {  // rank above: its last r rows (padded rows [H_up, H_up + r)) are this rank's padded rows [0, r)
+        src.list[1] = nf_list(d, d->peer[0].flags);
+        src.row_lo[1] = d->peer[0].H; src.row_hi[1] = d->peer[0].H + r; src.row_shift[1] = -d->peer[0].H;
+    }
+    if (d->peer[1].rec) {  // rank below: its first r rows (padded rows [r, 2r)) are this rank's padded rows [H + r, H + 2r)
+        src.list[2] = nf_list(d, d->peer[1].flags);
+        src.row_lo[2] = r; src.row_hi[2] = 2 * r; src.row_shift[2] = d->H;
+    }
+    return smc_launch_nonfinite_fixup(d->ctx, p, src);
+}
+
 // filter over output rows [y0, y1)
 static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo = nullptr) {
     SMC_CUDA(cudaSetDevice(d->ctx->device));
     if (y1 <= y0) return SMC_OK;
     SmcFilterParams p;
     fill_filter_params(d, p);
-    if (halo) p.halo = *halo;
+    SmcHaloSync release;
+    std::memset(&release, 0, sizeof(release));
+    if (halo) {  // the filter kernel waits for the halo rows; the fix-up kernel after it releases them
+        p.halo = *halo;
+        p.halo.signal0 = p.halo.signal1 = nullptr;
+        release = *halo;
+        release.wait0 = release.wait1 = nullptr;
+    }
     p.row_begin = y0;
     p.row_end = y1;
     if (d->use_sym) {
@@ -507,16 +547,17 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
         const char *nm = nullptr;
         const int rc = smc_launch_filter_sym(d->ctx, p, g, smem, &nm);
         if (nm) snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", nm);
-        return rc;
+        return rc ? rc : nonfinite_fixup(d, p, release);
     }
     if (d->use_stream) {
         const char *nm = nullptr;
         const int rc = smc_launch_filter_stream(d->ctx, p, d->d_rowrange, d->py, &nm);
         if (nm) snprintf(d->kernel_name, sizeof(d->kernel_name), "%s", nm);
-        return rc;
+        return rc ? rc : nonfinite_fixup(d, p, release);
     }
     snprintf(d->kernel_name, sizeof(d->kernel_name), "generic<C=%d,NG=%d,%s>", d->C, d->NG, d->mode ? "moon" : "welch");
-    return smc_launch_filter_generic(d->ctx, p);
+    const int rc = smc_launch_filter_generic(d->ctx, p);
+    return rc ? rc : nonfinite_fixup(d, p, release);
 }
 
 static int check_rows(const smc_denoiser *d, int y0, int y1, int lo, int hi) {

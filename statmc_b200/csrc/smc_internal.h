@@ -135,6 +135,31 @@ __device__ __forceinline__ void smc_halo_signal_last(const SmcHaloSync &h, int t
     }
 }
 
+// Non-finite values (a NaN or +-Inf radiance in the plane being filtered).  The reference SKIPS rejected taps and taps outside
+// the disc (stat_denoiser.cu:247-268), so a non-finite value only reaches the centres it is a member tap of; the streaming
+// kernels instead give such taps weight 0, and 0 * Inf = NaN would reach every centre of the window.  The prepass therefore
+// stores 0 in the record for a non-finite value and lists the position; after the filter a fix-up kernel adds w * value to
+// exactly the centres whose reference loop would have added it (smc_filter_fixup.cu).  The lists live behind the halo flags in
+// the record allocation, two of them (step parity) so that a neighbouring rank can read the entries of its halo rows while
+// this rank already lists the next frame.
+#define SMC_NF_CAP 16384
+struct SmcNfEntry {
+    int pr, pc, z, mask;  // padded record row / column, record image, bit j set: value j is non-finite
+    float v[4];           // values j = 0..2: record slots 8, 9, 6 (RGB value / film, or the three images of a triple);
+                          // j = 3: slot 4, the scalar value of a one-image scalar record
+};
+struct SmcNfList {
+    int count, pad[7];
+    SmcNfEntry e[SMC_NF_CAP];
+};
+#define SMC_NF_OFFSET 256  // bytes from the halo flags to SmcNfList[2]
+// what the fix-up kernel reads: this rank's list and, with peer halos, the neighbours' (entries of the rows that were stored
+// into this rank's halo, shifted to this rank's padded rows)
+struct SmcNfSources {
+    const SmcNfList *list[3];
+    int row_lo[3], row_hi[3], row_shift[3];  // take entries with row_lo <= pr < row_hi; this rank's padded row = pr + row_shift
+};
+
 // filter parameters shared by the kernels (passed by value)
 struct SmcFilterParams {
     int W, H;              // local plane size
@@ -223,12 +248,15 @@ struct SmcPrepassParams {
     float g_scale[SMC_MAX_GBUF_CHANNELS];
     const SmcPtrStepSz *mean_corr, *disc;  // optional tables (device) or null
     const float *lut;
+    SmcNfList *nf;  // where non-finite values are listed (see SmcNfEntry)
 };
 
 int smc_launch_prepass(smc_context *ctx, const SmcPrepassParams &p);
 int smc_launch_halo_signal(smc_context *ctx, int *f0, int *f1, int value);
 int smc_launch_halo_wait(smc_context *ctx, const int *f0, const int *f1, int value);
 int smc_launch_filter_generic(smc_context *ctx, const SmcFilterParams &p);
+// adds the listed non-finite values to the outputs of rows [row_begin, row_end) (after any of the filter kernels)
+int smc_launch_nonfinite_fixup(smc_context *ctx, const SmcFilterParams &p, const SmcNfSources &src);
 // returns SMC_ERR_UNSUPPORTED when the configuration has no streaming instantiation.
 // rowrange: device array, one {jlo, jhi} per spatial-table row; py: output rows per thread (2 or 4)
 int smc_launch_filter_stream(smc_context *ctx, const SmcFilterParams &p, const int2 *rowrange, int py,

@@ -231,6 +231,30 @@ __device__ __forceinline__ void prepass_finish(const SmcPrepassParams &p, float 
     // filter's packed accumulation (num.z += w * V.z, den += w * 1 in one FFMA2; smc_filter_stream.cu)
     if (NG < 7) rec[7] = 1.f;
 
+    // non-finite values: 0 in the record, listed for the fix-up pass (SmcNfEntry); when the list is full the value stays and
+    // the streaming kernels spread NaN over the whole window of the pixel instead of its member taps only
+    {
+        constexpr int vslot[4] = {8, 9, 6, 4};
+        const int nv = (p.C == 1 && !p.triple) ? 4 : 3;
+        int mask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < nv && (__float_as_uint(rec[vslot[j]]) & 0x7f800000u) == 0x7f800000u) mask |= 1 << j;
+        if (mask) {
+            const int idx = atomicAdd(&p.nf->count, 1);
+            if (idx < SMC_NF_CAP) {
+                SmcNfEntry e;
+                e.pr = pr; e.pc = pc; e.z = z; e.mask = mask;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    e.v[j] = rec[vslot[j]];
+                    if (mask >> j & 1) rec[vslot[j]] = 0.f;
+                }
+                p.nf->e[idx] = e;
+            }
+        }
+    }
+
     const size_t row_bytes = smc_rec_row_bytes(p.rec_pitch);
     unsigned char *row = p.rec + (size_t)z * p.rec_image_stride + (size_t)pr * row_bytes;
 #pragma unroll

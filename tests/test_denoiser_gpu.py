@@ -95,6 +95,50 @@ def test_nan_pixels_pass_through(ctx):
         assert rel_mad(ours["film_f"], ora["film_f"]) <= TOL
 
 
+def _poison(b):
+    """Non-finite radiance values: a NaN pixel whose statistics are NaN too (what a NaN sample leaves behind: no pair with it
+    passes the test), an Inf in one channel of pixels with ordinary statistics (member taps of their neighbours), the same at
+    a corner (replicated border copies), on the last row and on both sides of the band boundary of the two-rank tests."""
+    b = {k: v.copy() for k, v in b.items()}
+    H, W = b["n"].shape
+    b["film"][10, 12] = np.nan
+    b["mean"][10, 12] = np.nan
+    b["film"][H // 4, 40, 1] = np.inf
+    b["film"][0, 0, 0] = -np.inf
+    b["film"][H - 1, W - 3] = np.nan
+    b["film"][H // 2 - 1, 20, 2] = np.inf
+    b["film"][H // 2, 33] = np.nan
+    b["film"][H // 2 + 2, W - 1, 0] = -np.inf
+    return b
+
+
+def _same_nonfinite(got, ref):
+    return (np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isposinf(got), np.isposinf(ref)) and
+            np.array_equal(np.isneginf(got), np.isneginf(ref)))
+
+
+def _check_poisoned(got, b, r, sd):
+    # the reference skips rejected taps and taps outside the disc (stat_denoiser.cu:247-268): a non-finite value reaches the
+    # centres it is a member tap of, no others.  float32 oracle for WHICH pixels (its expf underflows where the kernels' does)
+    ref32 = po.denoise(b, radius=r, sd=sd, precision="f32")
+    ref64 = po.denoise(b, radius=r, sd=sd, precision="f64")
+    bad = ~np.isfinite(ref32)
+    assert bad.any() and bad.mean() < 0.2
+    assert _same_nonfinite(got, ref32)
+    ok = ~bad & np.isfinite(ref64)
+    assert rel_mad(got[ok], ref64[ok]) <= TOL
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_nonfinite_values_reach_member_taps_only(ctx, kernel):
+    W, H, r, sd = 150, 64, 8, 4.0
+    b = _poison(synth.moment_buffers(W, H, n=32, config_id=61))
+    _check_poisoned(denoise_host(ctx, b, radius=r, sd=sd, kernel=kernel)["film_f"], b, r, sd)
+    # a clean frame after a poisoned one through the same kind of plan: nothing is left over
+    b2 = synth.moment_buffers(W, H, n=32, config_id=62)
+    assert np.isfinite(denoise_host(ctx, b2, radius=r, sd=sd, kernel=kernel)["film_f"]).all()
+
+
 @pytest.mark.parametrize("names", [(), ("normal",), ("normal", "albedo", "depth"), ("depth",), ("depth", "albedo"),
                                    ("depth", "normal"), ("depth", "depth"), ("normal", "depth", "depth")])
 def test_gbuffer_sets(ctx, names):
@@ -266,6 +310,8 @@ def test_scalar_image_triples(ctx, monkeypatch, pc, W, H, r, names):
     ch = lambda k, a: np.ascontiguousarray(a[..., k % 3])
     up = lambda a: Buffer.from_array(ctx, a)
     dev = [{q: up(ch(k, s[q])) for q in ("mean", "m2", "m3")} for k, s in enumerate(src)]
+    for k, v in ((1, np.nan), (pc - 1, np.inf)):  # non-finite values stay within their image and its member taps
+        src[k]["film"][H // 2, W // 3 + k, k % 3] = v
     ns, vals = [up(s["n"]) for s in src], [up(ch(k, s["film"])) for k, s in enumerate(src)]
     gsrc = src[0]
     g = [up(gsrc[k]) for k in names]
@@ -285,13 +331,18 @@ def test_scalar_image_triples(ctx, monkeypatch, pc, W, H, r, names):
         dn.close()
     for k in range(pc):
         # same arithmetic; the mirror sums are grouped by other work units, hence summed in another order
-        assert _same_rows(res["1"][0][k], res["0"][0][k], 3)
+        a, b = res["1"][0][k], res["0"][0][k]
+        assert _same_nonfinite(a, b)
+        assert _same_rows(np.where(np.isfinite(a), a, 0), np.where(np.isfinite(b), b, 0), 3)
         assert bits_equal(res["1"][1][k], res["0"][1][k]) and bits_equal(res["1"][2][k], res["0"][2][k])
     for k, s in enumerate(src):
         mc, dc = po.prepass(s["n"], ch(k, s["mean"]), ch(k, s["m2"]), ch(k, s["m3"]))
         ref = po.filter(ch(k, s["film"]), [gsrc[q] for q in names], f, r, po.f32_factor(r / 2.0), mean_corr=mc, disc=dc,
                         precision="f64")
-        ok = s["n"] >= 2
+        ref32 = po.filter(ch(k, s["film"]), [gsrc[q] for q in names], f, r, po.f32_factor(r / 2.0), mean_corr=mc, disc=dc,
+                          precision="f32")
+        assert _same_nonfinite(res["1"][0][k], ref32) and (~np.isfinite(ref32)).any() == (k in (1, pc - 1))
+        ok = (s["n"] >= 2) & np.isfinite(ref32) & np.isfinite(ref)
         assert rel_mad(res["1"][0][k][ok], ref[ok]) <= TOL, k
 
 
@@ -442,8 +493,10 @@ def test_peer_halo_mode(ctx, kernel):
         plans.append((dn, out, dev, y0, y1))
     plans[0][0].peer_attach_local(1, plans[1][0])
     plans[1][0].peer_attach_local(0, plans[0][0])
-    for step, cfg in enumerate((52, 53)):
+    for step, cfg in enumerate((52, 53, 54, 55)):
         b = synth.moment_buffers(W, H, n=32, config_id=cfg)
+        if step == 2:  # non-finite values on both sides of the band boundary: they cross it like any other tap
+            b = _poison(b)
         full = denoise_host(ctx, b, radius=r, sd=sd, kernel=2)["film_f"]
         for dn, out, dev, y0, y1 in plans:
             for k, buf in dev.items():
@@ -454,7 +507,10 @@ def test_peer_halo_mode(ctx, kernel):
             dn.filter()
         ctx.synchronize()
         got = np.concatenate([plans[0][1].download(), plans[1][1].download()], axis=0)
-        assert _same_rows(got, full, kernel), step
+        assert _same_nonfinite(got, full), step
+        fin = np.isfinite(full)
+        assert (~fin).any() == (step == 2)
+        assert _same_rows(np.where(fin, got, 0), np.where(fin, full, 0), kernel), step
     for dn, *_ in plans:
         dn.close()
 
