@@ -287,6 +287,28 @@ int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_count, int 
                              void *film_filtered_ptrs, void *film_filtered_data, size_t film_filtered_step,
                              void *stream);
 
+/* The same call while (some of) the planes behind the tables are still on the host: `uploads` lists host -> device copies
+ * that have NOT been issued yet (the link shim defers Estimator::Upload's GpuMat::upload calls, EST.cpp:409-432).  Planes of
+ * `height` rows travel inside the row-chunked pipeline of smc_denoiser_run_host, so that PCIe overlaps the kernels although the
+ * reference calls Upload(); Denoise(); Download(); one after the other (statpath.cpp:406-418); other entries are copied up
+ * front.  Host memory should be page-locked (smc_host_alloc) and must stay unchanged until the stream has been synchronised.
+ * n_uploads == 0 is smc_filter_device_tables. */
+typedef struct smc_host_rows {
+    void *dev;         /* destination plane */
+    size_t dev_step;   /* bytes per device row */
+    const void *host;  /* source rows */
+    size_t host_step;  /* bytes per host row (0: tightly packed) */
+    size_t row_bytes;  /* bytes to copy per row */
+    int rows;
+} smc_host_rows;
+int smc_filter_device_tables_host(smc_context *ctx, int channels, int ptr_count, int width, int height, float ds_factor,
+                                  int radius, int denoise_film, const void *n_ptrs, const void *mean_ptrs,
+                                  const void *m2_ptrs, const void *m3_ptrs, const void *film_ptrs, const void *film_data,
+                                  size_t film_step, const void *gbuf_ptrs, const void *gbuf_channel_counts,
+                                  const void *gbuf_dr_factors, int n_gbufs, void *mean_corr_ptrs, void *disc_ptrs,
+                                  void *film_filtered_ptrs, void *film_filtered_data, size_t film_filtered_step,
+                                  void *stream, const smc_host_rows *uploads, int n_uploads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,13 +62,31 @@ void check(int rc, const char *what) {
 }
 
 #ifndef SMC_SHIM_HOST_ONLY
+// A GpuMat::upload of a page-locked plane that has not been issued yet.  Estimator::Upload (EST.cpp:409-432) uploads every
+// plane and Estimator::Denoise runs the filter right after it (statpath.cpp:406-418); holding the copies back until the filter
+// call lets the library move them inside its row-chunked pipeline, PCIe overlapping the kernels (smc_filter_device_tables_host).
+// Anything else that could observe the device plane or release the host memory issues the held copies first.
+// STATMC_B200_DEFER_UPLOADS=0 copies at once, as GpuMat::upload does.
+struct Pending {
+    smc_buffer *buf;
+    void *dev;
+    size_t dev_step;
+    const void *host;
+    size_t host_step, row_bytes;
+    int rows;
+    const void *host_owner;  // the cv::UMatData the rows belong to
+};
 struct Shim {
     smc_context *ctx = nullptr;
     std::mutex mu;
     std::unordered_map<const void *, smc_buffer *> owner;  // GpuMat::datastart -> the smc_buffer that owns the memory
+    std::vector<Pending> pending;
+    bool defer = true;
     Shim() {
         const char *d = std::getenv("STATMC_B200_DEVICE");
         check(smc_context_create(d ? std::atoi(d) : 0, &ctx), "smc_context_create");
+        const char *f = std::getenv("STATMC_B200_DEFER_UPLOADS");
+        defer = !(f && std::atoi(f) == 0);
     }
 };
 Shim &shim() {
@@ -80,6 +98,30 @@ smc_buffer *owner_of(const void *dev) {
     std::lock_guard<std::mutex> g(s.mu);
     auto it = s.owner.find(dev);
     return it == s.owner.end() ? nullptr : it->second;
+}
+std::vector<Pending> pending_take() {
+    Shim &s = shim();
+    std::lock_guard<std::mutex> g(s.mu);
+    std::vector<Pending> v;
+    v.swap(s.pending);
+    return v;
+}
+void pending_flush() {  // issue every held copy on the context stream
+    for (const Pending &p : pending_take()) check(smc_buffer_upload(p.buf, p.host, p.host_step), "GpuMat::upload (deferred)");
+}
+void pending_drop(const void *dev) {  // the device plane goes away or is about to be overwritten by a newer upload
+    Shim &s = shim();
+    std::lock_guard<std::mutex> g(s.mu);
+    for (size_t i = 0; i < s.pending.size();)
+        if (s.pending[i].dev == dev) s.pending.erase(s.pending.begin() + i);
+        else i++;
+}
+bool pending_reads(const void *host_owner) {
+    Shim &s = shim();
+    std::lock_guard<std::mutex> g(s.mu);
+    for (const Pending &p : s.pending)
+        if (p.host_owner == host_owner) return true;
+    return false;
 }
 
 #endif  // SMC_SHIM_HOST_ONLY
@@ -109,6 +151,12 @@ cv::UMatData *host_new(size_t bytes) {
     return u;
 }
 void host_delete(cv::UMatData *u) {
+#ifndef SMC_SHIM_HOST_ONLY
+    if (u->userdata && pending_reads(u)) {  // a held upload still reads these rows
+        pending_flush();
+        smc_synchronize(shim().ctx);
+    }
+#endif
     if (u->userdata)
         smc_host_free(u->origdata);
     else
@@ -197,6 +245,7 @@ public:
     }
     void free(cv::cuda::GpuMat *mat) override {
         smc_buffer *b = nullptr;
+        pending_drop(mat->datastart);
         {
             Shim &s = shim();
             std::lock_guard<std::mutex> g(s.mu);
@@ -485,7 +534,12 @@ void GpuMat::upload(InputArray arr, Stream &) {
     create(m.rows, m.cols, m.type());
     const Plane2D p = plane_of(*this);
     const size_t dev_row = ((p.row_bytes + 3) / 4) * 4;  // byte matrices live in whole words on the device (ShimAllocator)
-    if (dev_row == p.row_bytes) {
+    pending_drop(datastart);
+    Shim &s = shim();
+    if (s.defer && dev_row == p.row_bytes && m.u && m.u->userdata && p.row_bytes * (size_t)m.rows >= kPinnedFrom) {
+        std::lock_guard<std::mutex> g(s.mu);
+        s.pending.push_back(Pending{p.buf, data, step, m.data, m.step.p[0], p.row_bytes, m.rows, m.u});
+    } else if (dev_row == p.row_bytes) {
         check(smc_buffer_upload(p.buf, m.data, m.step.p[0]), "GpuMat::upload");
     } else {  // pad the rows on the way (pageable source: the copy is staged before the call returns)
         std::vector<uchar> tmp(dev_row * (size_t)m.rows, 0);
@@ -495,11 +549,13 @@ void GpuMat::upload(InputArray arr, Stream &) {
 }
 void GpuMat::upload(InputArray arr) {
     upload(arr, Stream::Null());
+    pending_flush();
     check(smc_synchronize(shim().ctx), "GpuMat::upload");
 }
 
 void GpuMat::download(OutputArray _dst, Stream &) const {
     if (!data) fail("GpuMat::download of an empty matrix");
+    pending_flush();
     Mat &dst = out_mat(_dst, rows, cols, type());
     const Plane2D p = plane_of(*this);
     const size_t dev_row = ((p.row_bytes + 3) / 4) * 4;
@@ -529,7 +585,10 @@ Stream &Stream::Null() {
     static Stream *s = new Stream;
     return *s;
 }
-void Stream::waitForCompletion() { check(smc_synchronize(impl_->ctx), "Stream::waitForCompletion"); }
+void Stream::waitForCompletion() {
+    pending_flush();
+    check(smc_synchronize(impl_->ctx), "Stream::waitForCompletion");
+}
 void *Stream::cudaPtr() const { return smc_context_stream(impl_->ctx); }
 
 // ---- the denoiser -----------------------------------------------------------------------------------------------------
@@ -575,12 +634,16 @@ struct ChannelsOf< ::float3> {
 
 void setup() { (void)shim(); }  // SD.cu:352-355 sets a malloc-heap limit and a cache preference; nothing of that is needed
 
-void synchronize(Stream &) { check(smc_synchronize(shim().ctx), "stat_denoiser::synchronize"); }
+void synchronize(Stream &) {
+    pending_flush();
+    check(smc_synchronize(shim().ctx), "stat_denoiser::synchronize");
+}
 
 template <typename T>
 void calculateMeanVars(const unsigned short ptrCount, const unsigned short width, const unsigned short height,
                        const PtrStepSzb &nPtrs, const PtrStepSzb &m2Ptrs, PtrStepSzb meanVarPtrs, Stream &) {
     Shim &s = shim();
+    pending_flush();
     check(smc_calculate_mean_vars_device_tables(s.ctx, ChannelsOf<T>::value, ptrCount, width, height, nPtrs.data, m2Ptrs.data,
                                                 meanVarPtrs.data, smc_context_stream(s.ctx)),
           "stat_denoiser::calculateMeanVars");
@@ -595,17 +658,21 @@ void filter(const unsigned short ptrCount, const unsigned short width, const uns
             PtrStepSzb filmFiltered, Stream &) {
     Shim &s = shim();
 #ifdef SMC_SHIM_REF_KERNELS
+    pending_flush();
     device::imgproc::stat_denoiser::filter<T>(ptrCount, width, height, dSFactor, radius, denoiseFilm, nPtrs, meanPtrs, m2Ptrs,
                                               m3Ptrs, filmPtrs, film, gBufferPtrs, gBufferChannelCounts, gBufferDRFactors, nGBufs,
                                               meanCorrPtrs, discriminatorPtrs, filmFilteredPtrs, filmFiltered,
                                               (CUstream_st *)smc_context_stream(s.ctx));
     return;
 #endif
-    check(smc_filter_device_tables(s.ctx, ChannelsOf<T>::value, ptrCount, width, height, dSFactor, radius, denoiseFilm,
-                                   nPtrs.data, meanPtrs.data, m2Ptrs.data, m3Ptrs.data, filmPtrs.data, film.data, film.step,
-                                   gBufferPtrs.data, gBufferChannelCounts.data, gBufferDRFactors.data, nGBufs, meanCorrPtrs.data,
-                                   discriminatorPtrs.data, filmFilteredPtrs.data, filmFiltered.data, filmFiltered.step,
-                                   smc_context_stream(s.ctx)),
+    // uploads held back since Estimator::Upload travel inside the filter's row-chunked pipeline
+    std::vector<smc_host_rows> ups;
+    for (const Pending &p : pending_take()) ups.push_back(smc_host_rows{p.dev, p.dev_step, p.host, p.host_step, p.row_bytes, p.rows});
+    check(smc_filter_device_tables_host(s.ctx, ChannelsOf<T>::value, ptrCount, width, height, dSFactor, radius, denoiseFilm,
+                                        nPtrs.data, meanPtrs.data, m2Ptrs.data, m3Ptrs.data, filmPtrs.data, film.data, film.step,
+                                        gBufferPtrs.data, gBufferChannelCounts.data, gBufferDRFactors.data, nGBufs,
+                                        meanCorrPtrs.data, discriminatorPtrs.data, filmFilteredPtrs.data, filmFiltered.data,
+                                        filmFiltered.step, smc_context_stream(s.ctx), ups.data(), (int)ups.size()),
           "stat_denoiser::filter");
 }
 

@@ -54,6 +54,12 @@ class HostIO(C.Structure):
                 ("mean_corr", C.POINTER(Plane)), ("disc", C.POINTER(Plane))]
 
 
+class HostRows(C.Structure):
+    """smc_host_rows: one deferred host -> device copy of smc_filter_device_tables_host"""
+    _fields_ = [("dev", C.c_void_p), ("dev_step", C.c_size_t), ("host", C.c_void_p), ("host_step", C.c_size_t),
+                ("row_bytes", C.c_size_t), ("rows", C.c_int)]
+
+
 class PeerInfo(C.Structure):
     _fields_ = [("ipc_handle", C.c_ubyte * 64), ("image_stride", C.c_uint64), ("flags_offset", C.c_uint64),
                 ("height", C.c_int32), ("radius", C.c_int32), ("rec_pitch", C.c_int32), ("ptr_count", C.c_int32),
@@ -118,6 +124,11 @@ SIGNATURES = {
                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smc_filter_device_tables_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                C.POINTER(HostRows), C.c_int]),
 }
 
 

@@ -519,6 +519,9 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
         // rows needs less)
         const size_t se = smc_filter_sym_scratch_elems(p, g), fe = (size_t)d->rec_images * (y1 - y0) * d->W;
         if (se > d->sym_scratch_elems || fe > d->sym_fwd_elems) {
+            // both arrays grow to the largest need seen so far (row chunks of different lengths alternate in the host pipeline,
+            // and a shorter chunk with shorter work units can need MORE scratch rows than a longer one: never shrink)
+            const size_t se2 = std::max(se, d->sym_scratch_elems), fe2 = std::max(fe, d->sym_fwd_elems);
             SMC_CUDA(cudaStreamSynchronize(d->ctx->stream));
             cudaFree(d->d_sym_scratch); cudaFree(d->d_sym_scratch_cnt); cudaFree(d->d_sym_fwd); cudaFree(d->d_sym_fwd_cnt);
             cudaFree(d->d_sym_scratch2); cudaFree(d->d_sym_fwd2);
@@ -526,7 +529,6 @@ static int filter_rows(smc_denoiser *d, int y0, int y1, const SmcHaloSync *halo 
             d->d_sym_scratch2 = d->d_sym_fwd2 = nullptr;
             d->d_sym_scratch_cnt = d->d_sym_fwd_cnt = nullptr;
             d->sym_scratch_elems = d->sym_fwd_elems = 0;
-            const size_t se2 = std::max(se, d->sym_scratch_elems), fe2 = std::max(fe, d->sym_fwd_elems);
             if (cudaMalloc(&d->d_sym_scratch, se2 * sizeof(float4)) != cudaSuccess ||
                 cudaMalloc(&d->d_sym_fwd, fe2 * sizeof(float4)) != cudaSuccess ||
                 (d->tri && (cudaMalloc(&d->d_sym_scratch2, se2 * sizeof(float2)) != cudaSuccess ||
@@ -669,17 +671,10 @@ static int auto_chunk_rows(const smc_denoiser *d) {
     return std::max(chunk, std::max(2 * d->radius, 16));
 }
 
-extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int chunk_rows) {
-    if (!d || !io) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
-    if (d->tables_external) SMC_FAIL(SMC_ERR_UNSUPPORTED, "plan was built from device tables: host planes unknown");
-    if (d->skip_top || d->skip_bottom)
-        SMC_FAIL(SMC_ERR_UNSUPPORTED, "record-halo exchange plans cannot be pipelined from the host in one call");
-    if (chunk_rows < 0) SMC_FAIL(SMC_ERR_INVALID, "chunk_rows < 0");
+// rows [bounds[k], bounds[k+1]) form chunk k of the host pipeline
+static void chunk_schedule(smc_denoiser *d, int chunk_rows, std::vector<int> &bounds) {
     smc_context *ctx = d->ctx;
-    SMC_CUDA(cudaSetDevice(ctx->device));
-    if (!d->s_in) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
-    if (!d->s_out) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
-    const int pc = d->ptr_count, H = d->H, r = d->radius;
+    const int H = d->H, r = d->radius;
     // Chunk boundaries: uniform, except for the last one (below).  (With the earlier, slower filter a schedule that ramped
     // up from a small first chunk and down to a small last one was measured SLOWER, 14.7 vs 14.1 ms at 4K: a filter launch
     // over few rows fills the persistent grid badly -- one tile is ~0.35 ms of work for a warp -- and compute, not PCIe, was
@@ -693,7 +688,6 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
     // copies and small launches cost what the shorter drain saves -- so it is off by default.
     const bool auto_chunks = chunk_rows == 0;
     if (chunk_rows == 0) chunk_rows = auto_chunk_rows(d);
-    std::vector<int> bounds;  // chunk k = rows [bounds[k], bounds[k+1])
     int unit = 0;             // rows of one wave of the streaming grid
     if (auto_chunks && d->use_stream) {
         SmcFilterParams fp;
@@ -743,34 +737,27 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
         if (bounds.back() < H) bounds.push_back(H);
     }
 
-    struct Xfer { const SmcPtrStepSz *dev; smc_plane host; size_t row_bytes; };
-    std::vector<Xfer> ups, downs;
-    auto add = [&](std::vector<Xfer> &v, const SmcPtrStepSz *dev, const smc_plane *host, size_t px_bytes) {
-        if (!host || !host->dev || !dev->data) return;
-        for (const Xfer &x : v)
-            if (x.dev->data == dev->data) return;  // aliased planes (mean == film-mean when !transform) move once
-        Xfer x{dev, *host, (size_t)d->W * px_bytes};
-        if (x.host.step == 0) x.host.step = x.row_bytes;
-        v.push_back(x);
-    };
-    const SmcPtrStepSz *T = d->h_tables.data();
-    const size_t cb = (size_t)d->C * 4;
-    for (int i = 0; i < pc; i++) {
-        add(ups, T + 0 * pc + i, io->n ? io->n + i : nullptr, 4);
-        add(ups, T + 1 * pc + i, io->mean ? io->mean + i : nullptr, cb);
-        add(ups, T + 2 * pc + i, io->m2 ? io->m2 + i : nullptr, cb);
-        add(ups, T + 3 * pc + i, io->m3 ? io->m3 + i : nullptr, cb);
-        add(ups, T + 4 * pc + i, io->film_ptrs ? io->film_ptrs + i : nullptr, cb);
-        add(downs, T + 5 * pc + i, io->mean_corr ? io->mean_corr + i : nullptr, cb);
-        add(downs, T + 6 * pc + i, io->disc ? io->disc + i : nullptr, cb);
-    }
-    add(ups, &d->film, &io->film, 12);
-    for (int g = 0; g < d->n_gbufs; g++)
-        add(ups, T + 9 * (size_t)pc + g, io->gbufs ? io->gbufs + g : nullptr, (size_t)d->h_gch[g] * 4);
-    const size_t n_aux_downs = downs.size();  // mean-corr / discriminator rows are final right after the prepass
-    for (int i = 0; i < pc; i++) add(downs, T + 7 * pc + i, io->film_filtered_ptrs ? io->film_filtered_ptrs + i : nullptr, cb);
-    add(downs, &d->film_filtered, &io->film_filtered, 12);
+}
 
+// one plane's rows moving between host and device inside the pipeline
+struct Xfer {
+    unsigned char *dev;
+    size_t dev_step;
+    smc_plane host;
+    size_t row_bytes;
+};
+
+// The pipeline proper: chunk k is uploaded on the copy stream while chunk k-1 is prepassed and the rows whose window is complete
+// are filtered on the context stream; finished rows of `downs` go back on a third stream (the first n_aux_downs of them -- mean-
+// corr / discriminator planes -- are final right after the prepass).
+static int run_pipeline(smc_denoiser *d, const std::vector<Xfer> &ups, const std::vector<Xfer> &downs, size_t n_aux_downs,
+                        int chunk_rows) {
+    smc_context *ctx = d->ctx;
+    if (!d->s_in) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+    if (!d->s_out) SMC_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+    const int H = d->H, r = d->radius;
+    std::vector<int> bounds;
+    chunk_schedule(d, chunk_rows, bounds);
     size_t ev = 0;
     cudaEvent_t e_begin = get_event(d, ev++);
     if (!e_begin) SMC_FAIL(SMC_ERR_CUDA, "cudaEventCreate failed");
@@ -786,7 +773,7 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
     for (size_t ci = 0; ci + 1 < bounds.size(); ci++) {
         const int a = bounds[ci], b = bounds[ci + 1];
         for (const Xfer &x : ups)
-            SMC_CUDA(cudaMemcpy2DAsync(x.dev->data + (size_t)a * x.dev->step, x.dev->step,
+            SMC_CUDA(cudaMemcpy2DAsync(x.dev + (size_t)a * x.dev_step, x.dev_step,
                                        (const char *)x.host.dev + (size_t)a * x.host.step, x.host.step, x.row_bytes,
                                        b - a, cudaMemcpyHostToDevice, d->s_in));
         cudaEvent_t e_up = get_event(d, ev++), e_f = get_event(d, ev++);
@@ -815,7 +802,7 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
             const int y0 = i < n_aux_downs ? a : f_begin, y1 = i < n_aux_downs ? b : f_end;
             if (y1 <= y0) continue;
             SMC_CUDA(cudaMemcpy2DAsync((char *)x.host.dev + (size_t)y0 * x.host.step, x.host.step,
-                                       x.dev->data + (size_t)y0 * x.dev->step, x.dev->step, x.row_bytes, y1 - y0,
+                                       x.dev + (size_t)y0 * x.dev_step, x.dev_step, x.row_bytes, y1 - y0,
                                        cudaMemcpyDeviceToHost, d->s_out));
         }
         if (trace) {
@@ -845,6 +832,45 @@ extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int
         }
     }
     return SMC_OK;
+}
+
+extern "C" int smc_denoiser_run_host(smc_denoiser *d, const smc_host_io *io, int chunk_rows) {
+    if (!d || !io) SMC_FAIL(SMC_ERR_INVALID, "NULL argument");
+    if (d->tables_external) SMC_FAIL(SMC_ERR_UNSUPPORTED, "plan was built from device tables: host planes unknown");
+    if (d->skip_top || d->skip_bottom)
+        SMC_FAIL(SMC_ERR_UNSUPPORTED, "record-halo exchange plans cannot be pipelined from the host in one call");
+    if (chunk_rows < 0) SMC_FAIL(SMC_ERR_INVALID, "chunk_rows < 0");
+    smc_context *ctx = d->ctx;
+    SMC_CUDA(cudaSetDevice(ctx->device));
+    const int pc = d->ptr_count;
+    std::vector<Xfer> ups, downs;
+    auto add = [&](std::vector<Xfer> &v, const SmcPtrStepSz *dev, const smc_plane *host, size_t px_bytes) {
+        if (!host || !host->dev || !dev->data) return;
+        for (const Xfer &x : v)
+            if (x.dev == dev->data) return;  // aliased planes (mean == film-mean when !transform) move once
+        Xfer x{dev->data, dev->step, *host, (size_t)d->W * px_bytes};
+        if (x.host.step == 0) x.host.step = x.row_bytes;
+        v.push_back(x);
+    };
+    const SmcPtrStepSz *T = d->h_tables.data();
+    const size_t cb = (size_t)d->C * 4;
+    for (int i = 0; i < pc; i++) {
+        add(ups, T + 0 * pc + i, io->n ? io->n + i : nullptr, 4);
+        add(ups, T + 1 * pc + i, io->mean ? io->mean + i : nullptr, cb);
+        add(ups, T + 2 * pc + i, io->m2 ? io->m2 + i : nullptr, cb);
+        add(ups, T + 3 * pc + i, io->m3 ? io->m3 + i : nullptr, cb);
+        add(ups, T + 4 * pc + i, io->film_ptrs ? io->film_ptrs + i : nullptr, cb);
+        add(downs, T + 5 * pc + i, io->mean_corr ? io->mean_corr + i : nullptr, cb);
+        add(downs, T + 6 * pc + i, io->disc ? io->disc + i : nullptr, cb);
+    }
+    add(ups, &d->film, &io->film, 12);
+    for (int g = 0; g < d->n_gbufs; g++)
+        add(ups, T + 9 * (size_t)pc + g, io->gbufs ? io->gbufs + g : nullptr, (size_t)d->h_gch[g] * 4);
+    const size_t n_aux_downs = downs.size();  // mean-corr / discriminator rows are final right after the prepass
+    for (int i = 0; i < pc; i++) add(downs, T + 7 * pc + i, io->film_filtered_ptrs ? io->film_filtered_ptrs + i : nullptr, cb);
+    add(downs, &d->film_filtered, &io->film_filtered, 12);
+
+    return run_pipeline(d, ups, downs, n_aux_downs, chunk_rows);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -957,6 +983,26 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
                                         const void *gbuf_dr_factors, int n_gbufs, void *mean_corr_ptrs,
                                         void *disc_ptrs, void *film_filtered_ptrs, void *film_filtered_data,
                                         size_t film_filtered_step, void *stream) {
+    return smc_filter_device_tables_host(ctx, channels, ptr_count, width, height, ds_factor, radius, denoise_film, n_ptrs,
+                                         mean_ptrs, m2_ptrs, m3_ptrs, film_ptrs, film_data, film_step, gbuf_ptrs,
+                                         gbuf_channel_counts, gbuf_dr_factors, n_gbufs, mean_corr_ptrs, disc_ptrs,
+                                         film_filtered_ptrs, film_filtered_data, film_filtered_step, stream, nullptr, 0);
+}
+
+// The same call when (some of) the planes the tables point at are still on the host: `uploads` lists copies that have not been
+// issued yet (Estimator::Upload deferred by the link shim).  Planes of `height` rows travel inside the row-chunked pipeline of
+// smc_denoiser_run_host -- chunk k on the copy stream while chunk k-1 is prepassed and filtered -- so that PCIe overlaps the
+// kernels although the reference calls Upload(); Denoise(); one after the other (statpath.cpp:406-418); anything else in the
+// list is copied up front.
+extern "C" int smc_filter_device_tables_host(smc_context *ctx, int channels, int ptr_count, int width, int height,
+                                             float ds_factor, int radius, int denoise_film, const void *n_ptrs,
+                                             const void *mean_ptrs, const void *m2_ptrs, const void *m3_ptrs,
+                                             const void *film_ptrs, const void *film_data, size_t film_step,
+                                             const void *gbuf_ptrs, const void *gbuf_channel_counts,
+                                             const void *gbuf_dr_factors, int n_gbufs, void *mean_corr_ptrs,
+                                             void *disc_ptrs, void *film_filtered_ptrs, void *film_filtered_data,
+                                             size_t film_filtered_step, void *stream, const smc_host_rows *uploads,
+                                             int n_uploads) {
     if (!ctx) SMC_FAIL(SMC_ERR_INVALID, "ctx == NULL");
     int rc = validate_common(channels, ptr_count, width, height, radius, n_gbufs);
     if (rc) return rc;
@@ -965,8 +1011,21 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
     if (denoise_film && (!film_data || !film_filtered_data)) SMC_FAIL(SMC_ERR_INVALID, "denoiseFilm needs film buffers");
     if (n_gbufs > 0 && (!gbuf_ptrs || !gbuf_channel_counts || !gbuf_dr_factors))
         SMC_FAIL(SMC_ERR_INVALID, "NULL G-buffer table");
+    if (n_uploads < 0 || (n_uploads > 0 && !uploads)) SMC_FAIL(SMC_ERR_INVALID, "bad upload list");
     SMC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    std::vector<Xfer> ups;
+    for (int i = 0; i < n_uploads; i++) {
+        const smc_host_rows &u = uploads[i];
+        if (!u.dev || !u.host || u.rows <= 0 || u.row_bytes == 0) SMC_FAIL(SMC_ERR_INVALID, "upload %d incomplete", i);
+        if (u.rows == height) {
+            ups.push_back(Xfer{(unsigned char *)u.dev, u.dev_step, smc_plane{(void *)u.host, u.host_step ? u.host_step : u.row_bytes},
+                               u.row_bytes});
+        } else {
+            SMC_CUDA(cudaMemcpy2DAsync(u.dev, u.dev_step, u.host, u.host_step ? u.host_step : u.row_bytes, u.row_bytes, u.rows,
+                                       cudaMemcpyHostToDevice, s));
+        }
+    }
 
     // The kernel variant and the record packing depend on the G-buffer channel counts and range factors, which live on the
     // device.  They are read back on EVERY call (a few bytes; the reference's flow blocks in Synchronize() right after
@@ -1038,7 +1097,7 @@ extern "C" int smc_filter_device_tables(smc_context *ctx, int channels, int ptr_
     // run on the caller's stream
     cudaStream_t saved = ctx->stream;
     ctx->stream = s;
-    rc = smc_denoiser_run(d);
+    rc = ups.empty() ? smc_denoiser_run(d) : run_pipeline(d, ups, std::vector<Xfer>(), 0, 0);
     ctx->stream = saved;
     return rc;
 }

@@ -556,3 +556,29 @@ def test_device_table_plan_follows_table_contents(ctx):
         assert rel_mad(got, ref) <= TOL, sds
     a, c = run(0.1, 0.02), run(0.5, 0.3)
     assert rel_mad(a, c) > 1e-3  # the two settings really differ
+
+    # smc_filter_device_tables_host: the same call while the planes are still on the host (the link shim holds
+    # Estimator::Upload's copies back); they travel inside the row-chunked pipeline and the result is the same
+    from statmc_b200.api import PinnedArray
+    b2 = synth.moment_buffers(W, H, n=32, config_id=12)
+    pinned, ups = [], (capi.HostRows * len(names))()
+    for i, k in enumerate(names):
+        src = b2[k] if b2[k].ndim == 3 else b2[k][..., None]
+        pa = PinnedArray(src.shape, src.dtype)
+        pa.array[...] = src
+        pinned.append(pa)
+        dev[k].zero()
+        ups[i] = capi.HostRows(capi.lib.smc_buffer_dev(dev[k].h), dev[k].plane.step, pa.ptr, 0, W * src.shape[2] * 4,
+                               H if k != "albedo" else H // 2)
+    # a plane listed in two parts (anything that is not `height` rows is copied up front)
+    extra = capi.HostRows(capi.lib.smc_buffer_dev(dev["albedo"].h) + (H // 2) * dev["albedo"].plane.step, dev["albedo"].plane.step,
+                          pinned[-1].ptr + (H // 2) * W * 12, 0, W * 12, H - H // 2)
+    ups2 = (capi.HostRows * (len(names) + 1))(*ups, extra)
+    gf.upload(np.array([[po.f32_factor(0.1), po.f32_factor(0.02)]], dtype=np.float32))
+    capi.check(capi.lib.smc_filter_device_tables_host(
+        ctx.h, 3, 1, W, H, po.f32_factor(sd), r, 1, dv(t["n"]), dv(t["mean"]), dv(t["m2"]), dv(t["m3"]), dv(t["film"]),
+        dv(dev["film"]), dev["film"].plane.step, dv(tg), dv(gch), dv(gf), 2, dv(tmc), dv(tdc), dv(tout), dv(out),
+        out.plane.step, C.c_void_p(ctx.stream), ups2, len(names) + 1))
+    ctx.synchronize()
+    assert rel_mad(out.download(), po.denoise(b2, radius=r, sd=sd, precision="f64")) <= TOL
+    assert bits_equal(dev["mean"].download(), b2["mean"])

@@ -70,6 +70,28 @@ def test_scalar_gbuffers_against_reference_kernels(ctx, names):
         assert rm <= 1e-4
 
 
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref/libstatmc_ref.so not built (needs /root/reference)")
+def test_nonfinite_values_against_reference_kernels(ctx):
+    # NaN / Inf radiance values: the reference's loop skips rejected taps and taps outside the disc (stat_denoiser.cu:247-268),
+    # so they reach member taps only; the same pixels -- and the same kind of non-finite value -- must come out of every kernel
+    W, H, r, sd = 160, 72, 9, 4.0
+    b = synth.moment_buffers(W, H, n=32, config_id=74)
+    b["film"][10, 12] = np.nan
+    b["mean"][10, 12] = np.nan
+    b["film"][30, 40, 1] = np.inf
+    b["film"][0, 0, 0] = -np.inf
+    b["film"][H - 1, W - 3] = np.nan
+    b["film"][50, W - 1, 2] = np.inf
+    ref = _ref_denoise(ctx, b, r, sd)["film_f"]
+    bad = ~np.isfinite(ref)
+    assert bad.any() and bad.mean() < 0.2
+    for kernel in (1, 2, 3):
+        ours = denoise_host(ctx, b, radius=r, sd=sd, kernel=kernel)["film_f"]
+        for pred in (np.isnan, np.isposinf, np.isneginf):
+            assert np.array_equal(pred(ours), pred(ref)), (kernel, pred.__name__)
+        assert rel_mad(ours[~bad], ref[~bad]) <= 1e-4
+
+
 @pytest.mark.skipif(not po.ref_available(moon=True), reason="oracle/_ref/libstatmc_ref_moon.so not built")
 def test_against_reference_moon_build(ctx):
     from statmc_b200 import _capi as capi

@@ -38,7 +38,7 @@ def test_reference_objects_need_only_what_the_shim_defines():
     # and the finished library wants nothing but libstatmc_b200's C ABI (plus libc / libstdc++)
     und = _nm(os.path.join(REFDIR, "libstatmc_ref_estimator.so"), "-u", "-D")
     assert not [s for s in und if s.startswith("cv::") or "pbrt" in s]
-    assert {"smc_filter_device_tables", "smc_buffer_create", "smc_buffer_upload", "smc_buffer_download"} <= und
+    assert {"smc_filter_device_tables_host", "smc_buffer_create", "smc_buffer_upload", "smc_buffer_download"} <= und
 
 
 def test_shim_mat_semantics():

@@ -31,9 +31,10 @@ def test_reference_estimator_rgb_default(ctx, W, H, radius, sd, n, vary):
     assert rel_mad(got["film_f"], ora["film_f"]) <= 1e-4
     # t0-b0-film-mean-f shares the host matrix of film-f (estimator.cpp:143-144)
     assert bits_equal(got["film_mean_f"], got["film_f"])
-    # same bits as our own plan API on the same planes
+    # and what our own plan API gives on the same planes (the shim's held-back uploads travel through the row-chunked
+    # pipeline: the symmetric kernel then sums in another order)
     ours = denoise_host(ctx, b, radius=radius, sd=sd, want_aux=True)
-    assert bits_equal(got["film_f"], ours["film_f"])
+    assert rel_mad(got["film_f"], ours["film_f"]) <= 1e-6
 
 
 def test_reference_estimator_scalar_acrr_bounces(ctx):
