@@ -348,9 +348,22 @@ def run_denoise_leg(env, workload, steps, warmup, *, radius_override=0, want_e2e
         marks.append(step(timed=True))
     t_end.record()
     env.barrier()
-    clocks = sampler.stop() if sampler else None
     launches = ctx.launches - launches0
     ms_step = env.allmax(t_start.elapsed_time(t_end)) / steps
+    clocks = None
+    if sampler:
+        # nvidia-smi delivers a sample every 100 ms: a timed region shorter than a few periods (20 steps of 1.2 ms at N = 8)
+        # would end before the first one.  Keep the SAME load running, untimed, until the window is 400 ms long (the same
+        # number of extra steps on every rank: the halo protocol runs in lock-step), then read the samples.
+        extra = 0
+        if steps * ms_step < 400.0:
+            extra = int(min(4000, np.ceil((400.0 - steps * ms_step) / max(ms_step, 1e-3))))
+            for _ in range(extra):
+                step()
+            ctx.synchronize()
+            env.barrier()
+        clocks = sampler.stop()
+        clocks["window"] = "timed region" if extra == 0 else "timed region + %d untimed steps of the same load" % extra
     res = {"W": W, "H": H, "radius": radius, "sd": sd, "n": n, "rows": rows, "band_px": (y1 - y0) * W,
            "value": W * H / (ms_step * 1e-3) / 1e6, "ms_per_step": ms_step, "clocks": clocks, "launches": int(launches),
            "pre_ms": float(np.mean([a.elapsed_time(b) for a, b, _, _ in marks])),

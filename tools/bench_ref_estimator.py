@@ -14,8 +14,10 @@ W, H, r, sd, n = 3840, 2160, 20, 10.0, 64
 if len(sys.argv) > 1 and sys.argv[1] == "1080p":
     W, H = 1920, 1080
 b = synth.moment_buffers(W, H, n=n, config_id=3)
-res = po.ref_estimator_denoise(b, r, sd, reps=4)
+res = po.ref_estimator_denoise(b, r, sd, reps=8)
 ms = res["cuda_time_ns"] / 1e6
 print(json.dumps({"what": "reference Estimator::Upload+Denoise+Download+Synchronize on libstatmc_b200 (link shim)",
+                  "uploads": "held back until the filter call and moved inside its row-chunked pipeline"
+                  if os.environ.get("STATMC_B200_DEFER_UPLOADS", "1") != "0" else "issued by GpuMat::upload, as OpenCV does",
                   "width": W, "height": H, "radius": r, "ms": ms, "mpix_per_s": W * H / ms / 1e3,
                   "planes_registered": res["n_registered"]}))

@@ -36,7 +36,7 @@ done ;;
     ncu_accum) timeout 900 ncu --set full --clock-control none --import-source on -k regex:accumulate_stream -s 2 -c 1 -f -o gpurun_out/prof_accum python tools/bench_accum.py --dist heavy 16 > gpurun_out/ncu_accum.log 2>&1; tail -2 gpurun_out/ncu_accum.log ;;
     ref_estimator) timeout 600 python tools/bench_ref_estimator.py 2>&1 | tail -1 | tee gpurun_out/ref_estimator_4k.json ;;
     ref_estimator_ab) for v in 0 1 0 1; do echo -n "[defer=$v] "; STATMC_B200_DEFER_UPLOADS=$v timeout 600 python tools/bench_ref_estimator.py 2>&1 | tail -1 | tee gpurun_out/ref_estimator_4k_defer$v.json | cut -c100-260; done ;;
-    sanitizer) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_denoiser_gpu.py -m gpu -x -q --timeout 1200 -k "rgb_default or large_radius or gbuffer_sets or tiny or peer_halo or host_pipelined" 2>&1 | tail -6 ;;
+    sanitizer) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_denoiser_gpu.py -m gpu -x -q --timeout 1200 -k "rgb_default or large_radius or gbuffer_sets or tiny or peer_halo or host_pipelined or nonfinite or triples or device_table" 2>&1 | tail -6 ;;
     ncu_filter) timeout 900 ncu --set full --clock-control none --import-source on -k regex:filter_sym -s 3 -c 1 -f -o gpurun_out/prof_filter $QB --no-e2e --no-parity --steps 1 --warmup 3 > gpurun_out/ncu_filter.log 2>&1; tail -2 gpurun_out/ncu_filter.log ;;
     ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $QB --no-e2e --no-parity --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log ;;
     *) echo "unknown stage $stage" ;;
