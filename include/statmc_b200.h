@@ -176,6 +176,12 @@ int smc_calculate_mean_vars_device_tables(smc_context *ctx, int channels, int pt
 /* ---------------------------------------------------------------------------------------------------------
  * Stage 2: statistical denoiser.  Replaces cv::cuda::stat_denoiser::filter<T> (CIP.hpp:756-799; SD.cu:397-475:
  * johnson_mean_corrs_kernel -> mean_discriminators_kernel -> filter_kernel) and Estimator::Denoise (EST.cpp:427-489).
+ *
+ * Non-finite input: a NaN / +-Inf value in a filtered plane (film, film_ptrs[z]) reaches the output pixels whose reference
+ * loop adds it -- the centres that accept the pixel as a tap inside the disc, and the pixel itself -- and no others, as the
+ * `continue`s of SD.cu:247-268 have it (up to 16384 such values per frame and plan; beyond that the excess ones turn their
+ * whole window NaN).  Non-finite statistics only make the membership test fail, as in the reference.  With several scalar
+ * images and no denoise_film, three images share one internal record (same results as one by one).
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct smc_filter_desc {
     int channels;      /* 1 = filter<float>, 3 = filter<float3> */

@@ -14,6 +14,10 @@ for stage in "$@"; do
     bench_full) timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_full.err | tee gpurun_out/bench_full.json | python -c "$P" || tail -5 gpurun_out/bench_full.err ;;
     bench_ref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2>gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json | cut -c1-900 ;;
     bench_acrr) timeout 600 python bench.py --no-cpu-baseline --no-accum --no-8k --no-e2e --no-parity --steps 5 2>gpurun_out/bench_acrr.err | tee gpurun_out/bench_acrr.json | python -c 'import sys,json; print(json.dumps(json.loads(sys.stdin.readlines()[-1])["acrr"]))' || tail -5 gpurun_out/bench_acrr.err ;;
+    driver) # what the driver runs at round end: smoke, the reference arm, the default bench line
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+      timeout 900 python bench.py --impl reference 2>gpurun_out/drv_ref.err | tee gpurun_out/drv_ref.json | cut -c1-300
+      timeout 900 python bench.py 2>gpurun_out/drv_bench.err | tee gpurun_out/drv_bench.json | python -c "$P" || tail -5 gpurun_out/drv_bench.err ;;
     sweep_*) # sweep_<ENVVAR>=v1:v2:...   device-resident bench per value
       kv=${stage#sweep_}; var=${kv%%=*}; vals=${kv#*=}
       for v in ${vals//:/ }; do echo -n "[$var=$v] "; env $var=$v timeout 300 $QB --no-e2e --no-parity --steps 10 2>gpurun_out/sweep.err | python -c "$P" || tail -3 gpurun_out/sweep.err; done ;;
