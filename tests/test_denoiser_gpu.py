@@ -470,6 +470,19 @@ def test_host_pipelined_run_is_exact(ctx, kernel, chunk):
         else:
             assert bits_equal(h_out.array, ref["film_f"]), (kernel, chunk, rep)
         assert bits_equal(h_mc.array, ref["mean_corr"]) and bits_equal(h_dc.array, ref["disc"])
+    # non-finite values cross chunk boundaries like any other tap (the fix-up pass runs per chunk on the values listed so
+    # far), and the next, clean frame starts from an empty list
+    bp = _poison(b)
+    refp = denoise_host(ctx, bp, radius=r, sd=sd, kernel=kernel)["film_f"]
+    for src, want in ((bp, refp), (b, ref["film_f"])):
+        for k in names:
+            pin[k].array[...] = src[k]
+        dn.run_host(n=[pin["n"]], mean=[pin["mean"]], m2=[pin["m2"]], m3=[pin["m3"]], film_ptrs=[pin["film"]],
+                    film=pin["film"], gbufs=[pin["normal"], pin["albedo"]], film_filtered=h_out, chunk_rows=chunk)
+        ctx.synchronize()
+        got, fin = h_out.array, np.isfinite(want)
+        assert _same_nonfinite(got, want), (kernel, chunk)
+        assert _same_rows(np.where(fin, got, 0), np.where(fin, want, 0), kernel), (kernel, chunk)
     dn.close()
 
 
