@@ -38,6 +38,7 @@ done ;;
     pipe_trace) SMC_PIPE_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus ${NGPU:-2} --steps 3 --warmup 3 --no-8k --no-accum 2> gpurun_out/pipe_trace_n${NGPU:-2}.txt | tail -1 | cut -c1-300 ;;
     ncu_step) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"filter_sym|sym_gather|prepass_kernel|nonfinite_fixup" -s 12 -c 4 -f -o gpurun_out/prof_step $QB --no-e2e --no-parity --steps 1 --warmup 3 > gpurun_out/ncu_step.log 2>&1; tail -2 gpurun_out/ncu_step.log ;;
     ncu_accum) timeout 900 ncu --set full --clock-control none --import-source on -k regex:accumulate_stream -s 2 -c 1 -f -o gpurun_out/prof_accum python tools/bench_accum.py --dist heavy 16 > gpurun_out/ncu_accum.log 2>&1; tail -2 gpurun_out/ncu_accum.log ;;
+    ncu_accum64) timeout 900 ncu --set full --clock-control none --import-source on -k regex:accumulate_stream -s 2 -c 1 -f -o gpurun_out/prof_accum64 python tools/bench_accum.py --dist heavy 64 > gpurun_out/ncu_accum64.log 2>&1; tail -2 gpurun_out/ncu_accum64.log ;;
     ref_estimator) timeout 600 python tools/bench_ref_estimator.py 2>&1 | tail -1 | tee gpurun_out/ref_estimator_4k.json ;;
     ref_estimator_ab) for v in 0 1 0 1; do echo -n "[defer=$v] "; STATMC_B200_DEFER_UPLOADS=$v timeout 600 python tools/bench_ref_estimator.py 2>&1 | tail -1 | tee gpurun_out/ref_estimator_4k_defer$v.json | cut -c100-260; done ;;
     sanitizer) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_denoiser_gpu.py -m gpu -x -q --timeout 1200 -k "rgb_default or large_radius or gbuffer_sets or tiny or peer_halo or host_pipelined or nonfinite or triples or device_table" 2>&1 | tail -6 ;;
