@@ -193,6 +193,55 @@ def test_streamed_path_constant_pixels_and_large_n(ctx, transform):
         assert bits_equal_nan(got[k], o[k]), (k, transform)
 
 
+def test_film_dividend_range_argument(ctx):
+    """The packed fast path divides d = x - mean and fD = s - filmMean by n with a shared-divisor division that is exact for
+    dividends that are 0 or at least 2^-78 (smc_moments.cu, header of accumulate_stream_kernel); d is covered by a range
+    argument, fD by a per-sample test.  Streams built against both -- samples around 2^-52, one small sample under hundreds of
+    zeros, samples equal to or one ulp away from the running film mean, samples that walk down into the denormals, negative
+    radiance followed by ordinary samples, and prior states with tiny or negative film means -- must stay bit-identical to the
+    CPU's IEEE update."""
+    W, H, C, S = 64, 8, 3, 3 * 160
+    rng = np.random.default_rng(4242)
+    f = np.float32
+    x = np.zeros((S, H, W, C), dtype=np.float32)
+    x[0, :, 0:8] = f(2.0 ** -52)                                   # one small sample, then zeros: the mean decays by 1 / n
+    x[0, :, 8:16] = f(2.0 ** -70)                                  # smaller still: its mean leaves the fast division's range
+    x[:, :, 16:24] = (2.0 ** rng.integers(-60, -44, size=(S, H, 8, C)) * rng.uniform(1, 2, size=(S, H, 8, C))).astype(f)
+    x[:, :, 24:32] = f(0.37)                                       # fD == 0 from the second sample on ...
+    x[S // 2:, :, 24:32] = np.nextafter(f(0.37), f(1))             # ... then one ulp off the running mean
+    x[:, :, 32:40] = rng.gamma(0.5, 2.0, size=(S, H, 8, C)).astype(f)
+    x[3, :, 32:40] = f(-0.5)                                       # negative radiance once
+    k = np.arange(S, dtype=np.float64)
+    x[:, :, 40:48] = (2.0 ** -np.minimum(k, 140))[:, None, None, None].astype(f) * f(1.5)   # walks down into the denormals
+    x[:, :, 48:56] = np.where(rng.random((S, H, 8, C)) < 0.7, 0.0, 2.0 ** rng.integers(-52, -48, size=(S, H, 8, C))).astype(f)
+    x[:, :, 56:64] = rng.gamma(0.25, 1.0, size=(S, H, 8, C)).astype(f)
+    x[7, 2, 60] = f(np.nan)
+    o = po.new_state(H, W, C)
+    # prior states: tiny, borderline and negative film means under a small and a large count
+    o["n"][4:] = 3
+    o["n"][6:] = 50000
+    o["film_mean"][4:, 0:16] = f(1e-30)
+    o["film_mean"][4:, 16:32] = f(2.0 ** -74)
+    o["film_mean"][4:, 32:48] = f(-0.25)
+    o["film_mean"][4:, 48:64] = f(0.125)
+    o["mean"][4:] = rng.normal(0, 0.5, size=(H - 4, W, C)).astype(f)
+    o["mean"][4:, 5:9] = f(3e-25)
+    o["m2"][4:] = rng.gamma(2.0, 1.0, size=(H - 4, W, C)).astype(f)
+    o["film_m2"][4:] = rng.gamma(2.0, 1.0, size=(H - 4, W, C)).astype(f)
+    st = MomentState(ctx, W, H, C, transform=True)
+    _upload_state(st, o)
+    before = ctx.accumulate_fallback_samples()
+    for part in (x[:160], x[160:320], x[320:]):
+        st.add_samples(part)
+        po.accumulate(o, part, transform=True, use_sqrt=True)
+    got = st.download()
+    assert np.array_equal(got["n"], o["n"].astype(np.int32))
+    for key in ("mean", "m2", "m3", "film_mean", "film_m2"):
+        assert bits_equal_nan(got[key], o[key]), key
+    # and the streams that are meant to stay on the packed path do: the scalar path took well under half of the updates
+    assert ctx.accumulate_fallback_samples() - before < 0.5 * S * H * W
+
+
 @pytest.mark.parametrize("name,cfg,z", accum_golden(), ids=[g[0] for g in accum_golden()])
 def test_accumulate_vs_reference_estimator_golden(ctx, name, cfg, z):
     """smc_accumulate against what the reference's OWN accumulation code produced (estimator.h:162-232 compiled
